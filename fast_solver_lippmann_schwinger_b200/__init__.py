@@ -1,0 +1,7 @@
+"""B200-native hot path of the fast Lippmann-Schwinger solver (libls_cuda.so + host mirror).
+
+Only what the path needs lives here: ``csrc/`` (CUDA kernels + the C ABI of include/ls_cuda.h),
+``_lib`` (ctypes binding) and ``operators`` / ``krylov`` (the reference's operator interface).
+"""
+from ._lib import (DeviceBuffer, LSCudaError, LSUnsupported, PinnedArray, declared_symbols, lib)  # noqa: F401
+from .operators import FastM, FFTconvolution, fastconvolution, mul_  # noqa: F401

@@ -1,0 +1,278 @@
+// Register-resident complex128 line-FFT engine for sm_100a.
+//
+// One line of N points (N = 2^6..2^12) is owned by T = N/E threads, E = 8 or 16 points per
+// thread.  Stages are radix 8/16 butterflies done entirely in registers; between stages
+// the points are exchanged through shared memory *in place* (stage i reads and writes the
+// same set of addresses per thread), so one __syncthreads() per exchange is enough and
+// the forward -> spectrum multiply -> inverse chain of the Lippmann-Schwinger apply never
+// needs a reorder:
+//   forward  = decimation in frequency: natural order in, "slot" order out;
+//   inverse  = the exact adjoint network: slot order in, natural order out.
+// The Green's spectrum is permuted once at create time into slot order, so no bit/digit
+// reversal ever runs on the device hot path.
+//
+// Shared-memory exchange patterns were checked bank-conflict free for every size with the
+// XOR swizzle below (128-bit accesses are served per quarter warp = 8 lanes).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace lsfft {
+
+typedef double2 cd;
+
+__device__ __forceinline__ cd cadd(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cd csub(cd a, cd b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cd cmul(cd a, cd b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__device__ __forceinline__ cd cmulc(cd a, cd b) {
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ cd cscale(cd a, double s) { return make_double2(a.x * s, a.y * s); }
+// a + b*c
+__device__ __forceinline__ cd cfma(cd b, cd c, cd a) {
+    return make_double2(a.x + (b.x * c.x - b.y * c.y), a.y + (b.x * c.y + b.y * c.x));
+}
+// a + b*conj(c)
+__device__ __forceinline__ cd cfmac(cd b, cd c, cd a) {
+    return make_double2(a.x + (b.x * c.x + b.y * c.y), a.y + (b.y * c.x - b.x * c.y));
+}
+
+// DIR = -1: forward kernel e^{-2 pi i jk/N};  DIR = +1: inverse (unnormalised).
+// multiply by DIR*i
+template <int DIR> __device__ __forceinline__ cd mul_i(cd a) {
+    if (DIR < 0) return make_double2(a.y, -a.x);
+    return make_double2(-a.y, a.x);
+}
+
+// multiply by exp(DIR * 2 pi i * K / 16), K compile time
+template <int DIR, int K> __device__ __forceinline__ cd mul_w16(cd a) {
+    constexpr int k = ((K % 16) + 16) % 16;
+    constexpr double c1 = 0.92387953251128673848;   // cos(pi/8)
+    constexpr double s1 = 0.38268343236508978178;   // sin(pi/8)
+    constexpr double h = 0.70710678118654752440;    // sqrt(1/2)
+    if (k == 0) return a;
+    if (k == 4) return mul_i<DIR>(a);
+    if (k == 8) return make_double2(-a.x, -a.y);
+    if (k == 12) return mul_i<-DIR>(a);
+    // general: w = cos(th) + DIR*i*sin(th), th = 2 pi k/16
+    constexpr double cs[16] = {1, c1, h, s1, 0, -s1, -h, -c1, -1, -c1, -h, -s1, 0, s1, h, c1};
+    constexpr double sn[16] = {0, s1, h, c1, 1, c1, h, s1, 0, -s1, -h, -c1, -1, -c1, -h, -s1};
+    constexpr double wr = cs[k];
+    constexpr double wi = (DIR < 0 ? -1.0 : 1.0) * sn[k];
+    if (k == 2 || k == 6 || k == 10 || k == 14) {
+        // |wr| == |wi| == h : two adds + two muls
+        constexpr double sr = wr > 0 ? 1.0 : -1.0;
+        constexpr double si = wi > 0 ? 1.0 : -1.0;
+        // (a.x + i a.y)(wr + i wi) = (a.x wr - a.y wi) + i (a.x wi + a.y wr)
+        return make_double2(h * (sr * a.x - si * a.y), h * (si * a.x + sr * a.y));
+    }
+    return make_double2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+}
+
+template <int DIR> __device__ __forceinline__ void dft2(cd& a0, cd& a1) {
+    cd t = a0;
+    a0 = cadd(t, a1);
+    a1 = csub(t, a1);
+}
+
+template <int DIR> __device__ __forceinline__ void dft4(cd& a0, cd& a1, cd& a2, cd& a3) {
+    cd t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    cd t2 = cadd(a1, a3), t3 = mul_i<DIR>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+// natural order in, natural order out
+template <int DIR> __device__ __forceinline__ void dft8(cd* v) {
+    // n = 2 n1 + n2 ; k = k1 + 4 k2
+    dft4<DIR>(v[0], v[2], v[4], v[6]);   // y0[k1] in v[0],v[2],v[4],v[6]
+    dft4<DIR>(v[1], v[3], v[5], v[7]);   // y1[k1] in v[1],v[3],v[5],v[7]
+    cd y1_1 = mul_w16<DIR, 2>(v[3]);
+    cd y1_2 = mul_w16<DIR, 4>(v[5]);
+    cd y1_3 = mul_w16<DIR, 6>(v[7]);
+    cd y0_0 = v[0], y0_1 = v[2], y0_2 = v[4], y0_3 = v[6], y1_0 = v[1];
+    v[0] = cadd(y0_0, y1_0); v[4] = csub(y0_0, y1_0);
+    v[1] = cadd(y0_1, y1_1); v[5] = csub(y0_1, y1_1);
+    v[2] = cadd(y0_2, y1_2); v[6] = csub(y0_2, y1_2);
+    v[3] = cadd(y0_3, y1_3); v[7] = csub(y0_3, y1_3);
+}
+
+template <int DIR> __device__ __forceinline__ void dft16(cd* v) {
+    // n = 4 n1 + n2 ; k = k1 + 4 k2
+    dft4<DIR>(v[0], v[4], v[8], v[12]);    // n2 = 0 : y[0][k1] at v[4 k1 + 0]
+    dft4<DIR>(v[1], v[5], v[9], v[13]);    // n2 = 1
+    dft4<DIR>(v[2], v[6], v[10], v[14]);   // n2 = 2
+    dft4<DIR>(v[3], v[7], v[11], v[15]);   // n2 = 3
+    // y[n2][k1] lives at v[4 k1 + n2]; twiddle W16^{n2 k1}
+    v[5] = mul_w16<DIR, 1>(v[5]);
+    v[6] = mul_w16<DIR, 2>(v[6]);
+    v[7] = mul_w16<DIR, 3>(v[7]);
+    v[9] = mul_w16<DIR, 2>(v[9]);
+    v[10] = mul_w16<DIR, 4>(v[10]);
+    v[11] = mul_w16<DIR, 6>(v[11]);
+    v[13] = mul_w16<DIR, 3>(v[13]);
+    v[14] = mul_w16<DIR, 6>(v[14]);
+    v[15] = mul_w16<DIR, 9>(v[15]);
+    // for each k1: 4-point DFT over n2 -> X[k1 + 4 k2] ; result k2 lands at v[4 k1 + k2]
+    dft4<DIR>(v[0], v[1], v[2], v[3]);
+    dft4<DIR>(v[4], v[5], v[6], v[7]);
+    dft4<DIR>(v[8], v[9], v[10], v[11]);
+    dft4<DIR>(v[12], v[13], v[14], v[15]);
+    // now v[4 k1 + k2] = X[k1 + 4 k2]: transpose the 4x4 register tile (pure renaming)
+    cd t;
+    t = v[1]; v[1] = v[4]; v[4] = t;
+    t = v[2]; v[2] = v[8]; v[8] = t;
+    t = v[3]; v[3] = v[12]; v[12] = t;
+    t = v[6]; v[6] = v[9]; v[9] = t;
+    t = v[7]; v[7] = v[13]; v[13] = t;
+    t = v[11]; v[11] = v[14]; v[14] = t;
+}
+
+template <int DIR, int R> __device__ __forceinline__ void dftR(cd* v) {
+    if (R == 16) dft16<DIR>(v);
+    else if (R == 8) dft8<DIR>(v);
+    else if (R == 4) dft4<DIR>(v[0], v[1], v[2], v[3]);
+    else dft2<DIR>(v[0], v[1]);
+}
+
+// ------------------------------------------------------------------------------------
+// size configuration: E points per thread, up to three stages (every radix is 8 or 16)
+// ------------------------------------------------------------------------------------
+template <int N> struct Cfg;
+template <> struct Cfg<64>   { static constexpr int E = 8,  S = 2, R0 = 8,  R1 = 8,  R2 = 1; };
+template <> struct Cfg<128>  { static constexpr int E = 16, S = 2, R0 = 16, R1 = 8,  R2 = 1; };
+template <> struct Cfg<256>  { static constexpr int E = 16, S = 2, R0 = 16, R1 = 16, R2 = 1; };
+template <> struct Cfg<512>  { static constexpr int E = 8,  S = 3, R0 = 8,  R1 = 8,  R2 = 8; };
+template <> struct Cfg<1024> { static constexpr int E = 16, S = 3, R0 = 16, R1 = 8,  R2 = 8; };
+template <> struct Cfg<2048> { static constexpr int E = 16, S = 3, R0 = 16, R1 = 16, R2 = 8; };
+template <> struct Cfg<4096> { static constexpr int E = 16, S = 3, R0 = 16, R1 = 16, R2 = 16; };
+
+constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
+template <int N, int I> struct Stage {
+    typedef Cfg<N> C;
+    static constexpr int E = C::E;
+    static constexpr int T = N / E;
+    static constexpr int R = (I == 0) ? C::R0 : (I == 1 ? C::R1 : C::R2);
+    static constexpr int PRE = (I == 0) ? 1 : (I == 1 ? C::R0 : C::R0 * C::R1);
+    static constexpr int Mprev = N / PRE;
+    static constexpr int M = Mprev / R;
+    static constexpr int NB = E / R;            // butterflies per thread
+    static constexpr bool LAST = (I == C::S - 1);
+    static constexpr int RLAST = (C::S == 2) ? C::R1 : C::R2;
+    // logical (unswizzled) in-place address of point a of butterfly u, thread t
+    __device__ __forceinline__ static int addr(int t, int u, int a) {
+        int beta = t + T * u;
+        int D = beta / M, b = beta % M;
+        return D * Mprev + a * M + b;
+    }
+    __device__ __forceinline__ static int bidx(int t, int u) { return (t + T * u) % M; }
+};
+
+// shared-memory layouts --------------------------------------------------------------
+// A: one line contiguous at `base`, XOR swizzle keyed on the last radix
+template <int N> struct LayA {
+    int base;
+    __device__ __forceinline__ int phys(int l) const {
+        constexpr int sh = ilog2(Stage<N, 0>::RLAST);
+        return base + (l ^ ((l >> sh) & 7));
+    }
+};
+// B: eight lines interleaved point by point (lane%8 = line) - conflict free by construction
+template <int N> struct LayB {
+    int lam;
+    __device__ __forceinline__ int phys(int l) const { return l * 8 + lam; }
+};
+
+template <int N, int I, class Lay>
+__device__ __forceinline__ void st_stage(const cd* v, int t, cd* sm, const Lay& lay) {
+    typedef Stage<N, I> St;
+#pragma unroll
+    for (int u = 0; u < St::NB; ++u)
+#pragma unroll
+        for (int a = 0; a < St::R; ++a) sm[lay.phys(St::addr(t, u, a))] = v[u * St::R + a];
+}
+template <int N, int I, class Lay>
+__device__ __forceinline__ void ld_stage(cd* v, int t, const cd* sm, const Lay& lay) {
+    typedef Stage<N, I> St;
+#pragma unroll
+    for (int u = 0; u < St::NB; ++u)
+#pragma unroll
+        for (int a = 0; a < St::R; ++a) v[u * St::R + a] = sm[lay.phys(St::addr(t, u, a))];
+}
+
+// butterflies (+ DIF twiddles) of stage I, forward
+template <int N, int I>
+__device__ __forceinline__ void fwd_stage(cd* v, int t, const cd* __restrict__ W) {
+    typedef Stage<N, I> St;
+#pragma unroll
+    for (int u = 0; u < St::NB; ++u) {
+        dftR<-1, St::R>(v + u * St::R);
+        if (!St::LAST) {
+            int b = St::bidx(t, u);
+#pragma unroll
+            for (int d = 1; d < St::R; ++d) {
+                cd w = __ldg(&W[(b * d) * (N / St::Mprev)]);
+                v[u * St::R + d] = cmul(v[u * St::R + d], w);
+            }
+        }
+    }
+}
+// adjoint of fwd_stage: conjugate twiddles, then inverse butterflies
+template <int N, int I>
+__device__ __forceinline__ void inv_stage(cd* v, int t, const cd* __restrict__ W) {
+    typedef Stage<N, I> St;
+#pragma unroll
+    for (int u = 0; u < St::NB; ++u) {
+        if (!St::LAST) {
+            int b = St::bidx(t, u);
+#pragma unroll
+            for (int d = 1; d < St::R; ++d) {
+                cd w = __ldg(&W[(b * d) * (N / St::Mprev)]);
+                v[u * St::R + d] = cmulc(v[u * St::R + d], w);
+            }
+        }
+        dftR<+1, St::R>(v + u * St::R);
+    }
+}
+
+// Forward FFT of one line.  In: v[a] = x[a*T + t].  Out: v[e] = X[freq(t + T*e)].
+// W = table exp(-2 pi i k/N), k < N.  sm/lay = this line's exchange buffer (N points).
+template <int N, class Lay>
+__device__ __forceinline__ void fft_fwd(cd* v, int t, cd* sm, const Lay& lay, const cd* __restrict__ W) {
+    typedef Cfg<N> C;
+    fwd_stage<N, 0>(v, t, W);
+    st_stage<N, 0>(v, t, sm, lay);
+    __syncthreads();
+    ld_stage<N, 1>(v, t, sm, lay);
+    fwd_stage<N, 1>(v, t, W);
+    if (C::S == 3) {
+        st_stage<N, 1>(v, t, sm, lay);
+        __syncthreads();
+        ld_stage<N, 2>(v, t, sm, lay);
+        fwd_stage<N, 2>(v, t, W);
+    }
+}
+
+// Unnormalised inverse FFT (adjoint network).  In: v[e] = X[freq(t + T*e)].  Out: v[a] = N*x[a*T + t].
+template <int N, class Lay>
+__device__ __forceinline__ void fft_inv(cd* v, int t, cd* sm, const Lay& lay, const cd* __restrict__ W) {
+    typedef Cfg<N> C;
+    if (C::S == 3) {
+        inv_stage<N, 2>(v, t, W);
+        st_stage<N, 2>(v, t, sm, lay);
+        __syncthreads();
+        ld_stage<N, 1>(v, t, sm, lay);
+    }
+    inv_stage<N, 1>(v, t, W);
+    st_stage<N, 1>(v, t, sm, lay);
+    __syncthreads();
+    ld_stage<N, 0>(v, t, sm, lay);
+    inv_stage<N, 0>(v, t, W);
+}
+
+}  // namespace lsfft

@@ -1,0 +1,204 @@
+// 2-D Lippmann-Schwinger operator  y = b + omega^2 * G (nu .* b)   on one B200.
+// Stands behind struct FastM and its `*` / mul! / fastconvolution / FFTconvolution methods
+// (reference FastConvolution.jl:11-154).  Three launches per apply:
+//   P1  k_fwd_pruned  columns (x, contiguous):  b, nu      -> A  [ne x m]   (slot order in x)
+//   P2  k_mid_fused   rows (y): A, Green spectrum          -> C  [m x ne]   (line contiguous)
+//   P3  k_inv_pruned  columns (x): C, b                    -> y
+// Algorithmic HBM bytes per apply: 568*N  (SURVEY.md section 8(d)).
+#include "ls_common.cuh"
+#include "line_kernels.cuh"
+
+using namespace ls;
+using namespace lsk;
+
+namespace {
+
+struct Op2D : HandleBase {
+    long n = 0, m = 0, ne = 0, me = 0;
+    double omega = 0;
+    int quadrule = 0;
+    double* d_nu = nullptr;
+    cd* d_G = nullptr;        // [sx][ry][slot_y], scaled by 1/(ne*me)
+    cd* d_Wn = nullptr; cd* d_Wm = nullptr;
+    cd* d_MODn = nullptr; cd* d_MODm = nullptr;
+    cd* d_A = nullptr;        // ne x m
+    cd* d_C = nullptr;        // m x ne (line contiguous)
+    cd* d_b = nullptr; cd* d_y = nullptr;   // staging for host-pointer applies
+    int64_t op_size() const override { return n * m; }
+};
+
+// Gd[(sx*4 + ry)*m + sy] = GFFT[(4 fx[sx%n] + sx/n + ne/2) % ne, (4 fy[sy] + ry + me/2) % me] / (ne*me)
+__global__ void k_permute_g2d(const cd* __restrict__ gin, cd* __restrict__ gout,
+                              const int* __restrict__ fx, const int* __restrict__ fy,
+                              long n, long m, long ne, long me, double scale) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = ne * me;
+    if (idx >= total) return;
+    long sy = idx % m;
+    long ry = (idx / m) % 4;
+    long sx = idx / (4 * m);
+    long kx = 4L * fx[sx % n] + sx / n;
+    long ky = 4L * fy[sy] + ry;
+    long ix = (kx + ne / 2) % ne, iy = (ky + me / 2) % me;
+    cd v = gin[ix + ne * iy];
+    gout[idx] = make_double2(v.x * scale, v.y * scale);
+}
+
+template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
+    constexpr int smem = smem_fwd<N, false>();
+    static bool attr = false;
+    if (!attr) {
+        LS_CUDA_TRY(cudaFuncSetAttribute(k_fwd_pruned<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
+    k_fwd_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
+        b, nu, op->d_A, op->d_Wn, op->d_MODn, op->n, 1, op->ne, 1, 0);
+    op->launches++;
+    return LS_OK;
+}
+template <int N> int launch_mid(Op2D* op) {
+    constexpr int smem = smem_mid<N, false>();
+    static bool attr = false;
+    if (!attr) {
+        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid((unsigned)(op->ne / GeoA<N>::LPC));
+    // line = x slot sx; point j at A[sx + ne*j]; output line contiguous C[j + m*sx]
+    k_mid_fused<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
+        op->d_A, op->d_C, op->d_G, op->d_Wm, op->d_MODm, 1, op->ne, op->m, 1, 0);
+    op->launches++;
+    return LS_OK;
+}
+template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
+    constexpr int smem = smem_fwd<N, false>();
+    static bool attr = false;
+    if (!attr) {
+        LS_CUDA_TRY(cudaFuncSetAttribute(k_inv_pruned<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
+    // line = column j; slot sx at C[j + m*sx]
+    k_inv_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
+        op->d_C, bsrc, y, op->d_Wn, op->d_MODn, scale, 1, op->m, op->n, 1, 0);
+    op->launches++;
+    return LS_OK;
+}
+
+#define LS_DISPATCH_N(N_, CALL)                                       \
+    switch (N_) {                                                     \
+        case 64:   rc = CALL(64); break;                              \
+        case 128:  rc = CALL(128); break;                             \
+        case 256:  rc = CALL(256); break;                             \
+        case 512:  rc = CALL(512); break;                             \
+        case 1024: rc = CALL(1024); break;                            \
+        case 2048: rc = CALL(2048); break;                            \
+        case 4096: rc = CALL(4096); break;                            \
+        default: rc = LS_ERR_UNSUPPORTED;                             \
+    }
+
+int apply_device(Op2D* op, const cd* b, cd* y, int mode) {
+    int rc = LS_OK;
+    const double* nu = (mode == LS_APPLY_FASTCONVOLUTION) ? op->d_nu : nullptr;   // Q2: GV FFTconvolution has no nu
+#define CALL_FWD(N) launch_fwd<N>(op, b, nu)
+    LS_DISPATCH_N(op->n, CALL_FWD);
+    if (rc) return rc;
+#define CALL_MID(N) launch_mid<N>(op)
+    LS_DISPATCH_N(op->m, CALL_MID);
+    if (rc) return rc;
+    const cd* bsrc = (mode == LS_APPLY_FASTCONVOLUTION) ? b : nullptr;
+    double scale = (mode == LS_APPLY_FASTCONVOLUTION) ? op->omega * op->omega : 1.0;
+#define CALL_INV(N) launch_inv<N>(op, bsrc, y, scale)
+    LS_DISPATCH_N(op->n, CALL_INV);
+    if (rc) return rc;
+    LS_CUDA_TRY(cudaGetLastError());
+    return LS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
+                   const double* nu, const ls_cdouble* gfft, double omega, int quadrule, int flags) {
+    (void)flags;
+    LS_REQUIRE(out && nu && gfft, LS_ERR_INVALID, "ls_op2d_create: null pointer");
+    LS_REQUIRE(n > 0 && m > 0 && ne > 0 && me > 0, LS_ERR_INVALID, "ls_op2d_create: non-positive size");
+    LS_REQUIRE(quadrule == LS_QUAD_TRAPEZOIDAL || quadrule == LS_QUAD_GREENGARD_VICO, LS_ERR_INVALID,
+               "ls_op2d_create: unknown quadRule %d", quadrule);
+    if (quadrule == LS_QUAD_TRAPEZOIDAL) {
+        LS_REQUIRE(ne == 2 * n - 1 && me == 2 * m - 1, LS_ERR_INVALID,
+                   "ls_op2d_create: trapezoidal needs ne = 2n-1, me = 2m-1 (FastConvolution.jl:183)");
+        LS_REQUIRE(false, LS_ERR_UNSUPPORTED,
+                   "ls_op2d_create: trapezoidal quadrature (odd, non power-of-two FFT sizes) is not served by the GPU path yet");
+    }
+    LS_REQUIRE(ne == 4 * n && me == 4 * m, LS_ERR_INVALID,
+               "ls_op2d_create: Greengard_Vico needs ne = 4n, me = 4m (FastConvolution.jl:201)");
+    LS_REQUIRE(fft_size_supported(n) && fft_size_supported(m), LS_ERR_UNSUPPORTED,
+               "ls_op2d_create: n=%ld, m=%ld - the GPU path serves powers of two in [64, 4096]", (long)n, (long)m);
+
+    Op2D* op = new Op2D();
+    int rc = op->init_base(KIND_OP2D);
+    if (rc) { delete op; return rc; }
+    op->n = n; op->m = m; op->ne = ne; op->me = me; op->omega = omega; op->quadrule = quadrule;
+    const size_t N = (size_t)n * m, NE = (size_t)ne * me;
+#define TRY(x) do { rc = (x); if (rc) { delete op; return rc; } } while (0)
+    TRY(op->dupload((void**)&op->d_nu, nu, N * sizeof(double)));
+    {
+        auto Wn = twiddle_table(n, n), Wm = twiddle_table(m, m);
+        auto Mn = modulation_table(n), Mm = modulation_table(m);
+        TRY(op->dupload((void**)&op->d_Wn, Wn.data(), Wn.size() * sizeof(cd)));
+        TRY(op->dupload((void**)&op->d_Wm, Wm.data(), Wm.size() * sizeof(cd)));
+        TRY(op->dupload((void**)&op->d_MODn, Mn.data(), Mn.size() * sizeof(cd)));
+        TRY(op->dupload((void**)&op->d_MODm, Mm.data(), Mm.size() * sizeof(cd)));
+    }
+    {
+        // one-time permutation of the spectrum into [x slot][ry][y slot] order, ifftshift folded in
+        auto fx = slot_freq((int)n), fy = slot_freq((int)m);
+        int *d_fx = nullptr, *d_fy = nullptr;
+        cd* d_gin = nullptr;
+        TRY(op->dupload((void**)&d_fx, fx.data(), fx.size() * sizeof(int)));
+        TRY(op->dupload((void**)&d_fy, fy.data(), fy.size() * sizeof(int)));
+        TRY(op->dupload((void**)&d_gin, gfft, NE * sizeof(cd)));
+        TRY(op->dmalloc((void**)&op->d_G, NE * sizeof(cd)));
+        const int th = 256;
+        k_permute_g2d<<<(unsigned)((NE + th - 1) / th), th, 0, op->stream>>>(
+            d_gin, op->d_G, d_fx, d_fy, n, m, ne, me, 1.0 / ((double)ne * (double)me));
+        cudaError_t e = cudaStreamSynchronize(op->stream);
+        if (e != cudaSuccess) { set_error("spectrum permutation failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
+        op->dfree(d_gin); op->dfree(d_fx); op->dfree(d_fy);
+    }
+    TRY(op->dmalloc((void**)&op->d_A, (size_t)ne * m * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_C, (size_t)ne * m * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_b, N * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_y, N * sizeof(cd)));
+#undef TRY
+    *out = reinterpret_cast<ls_handle>(op);
+    return LS_OK;
+}
+
+int ls_op2d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc) {
+    LS_REQUIRE(h && b && y, LS_ERR_INVALID, "ls_op2d_apply: null argument");
+    Op2D* op = reinterpret_cast<Op2D*>(h);
+    LS_REQUIRE(op->kind == KIND_OP2D, LS_ERR_INVALID, "ls_op2d_apply: not a 2-D operator handle");
+    LS_REQUIRE(mode == LS_APPLY_FASTCONVOLUTION || mode == LS_APPLY_FFTCONVOLUTION, LS_ERR_INVALID,
+               "ls_op2d_apply: unknown mode %d", mode);
+    if (mode == LS_APPLY_FFTCONVOLUTION)
+        LS_REQUIRE(op->n == op->m, LS_ERR_INVALID,
+                   "FFTconvolution pads (ne,ne) and crops (n,n): square grids only (FastConvolution.jl:139-151)");
+    LS_CUDA_TRY(cudaSetDevice(op->device));
+    const size_t bytes = (size_t)op->n * op->m * sizeof(cd);
+    if (memloc == LS_MEM_DEVICE) {
+        return apply_device(op, reinterpret_cast<const cd*>(b), reinterpret_cast<cd*>(y), mode);
+    }
+    LS_REQUIRE(memloc == LS_MEM_HOST, LS_ERR_INVALID, "ls_op2d_apply: unknown memloc %d", memloc);
+    LS_CUDA_TRY(cudaMemcpyAsync(op->d_b, b, bytes, cudaMemcpyHostToDevice, op->stream));
+    int rc = apply_device(op, op->d_b, op->d_y, mode);
+    if (rc) return rc;
+    LS_CUDA_TRY(cudaMemcpyAsync(y, op->d_y, bytes, cudaMemcpyDeviceToHost, op->stream));
+    LS_CUDA_TRY(cudaStreamSynchronize(op->stream));
+    return LS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+/* libls_cuda.so - C ABI of the B200-native Lippmann-Schwinger hot path.
+ *
+ * The reference (tanderson92/Fast_solver_Lippmann_Schwinger, pure Julia) has no FFI for
+ * this path; its boundary is Julia multiple dispatch on the operator objects.  Each entry
+ * point below names the reference method it stands behind (file:line under the reference's
+ * src/), and INTEGRATION.md shows the `ccall` stubs a maintainer adds on the Julia side
+ * (julia/LSCuda.jl).  The only ccall precedent upstream is sparseblas.jl:14-25
+ * (mkl_zcscmv_: y <- alpha*A*x + beta*y on CSC arrays), which ls_spm_mv mirrors.
+ *
+ * Conventions: complex128 = two doubles (re, im); arrays are Julia column-major, x fastest;
+ * sparse matrices arrive as Julia SparseMatrixCSC{ComplexF64,Int64} (1-based colptr /
+ * rowval).  Every function returns 0 (LS_OK) or a negative error code; ls_last_error()
+ * returns a thread-local message.  No C++ exception and no torch type crosses this ABI.
+ * Handles are opaque, not thread-safe, own their CUDA stream(s) and are freed by
+ * ls_destroy.  `memloc` tells whether data pointers are host or device memory.  Calls with
+ * host pointers are synchronous; calls with device pointers are enqueued on the handle's
+ * stream (ls_sync waits for it).  There is no CPU fallback anywhere in this library.
+ */
+#ifndef LS_CUDA_H
+#define LS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } ls_cdouble;
+typedef struct ls_handle_s* ls_handle;
+
+#define LS_OK               0
+#define LS_ERR_INVALID     -1   /* bad argument / shape mismatch (reference would throw DimensionMismatch) */
+#define LS_ERR_UNSUPPORTED -2   /* valid for the reference, not (yet) served by the GPU path */
+#define LS_ERR_CUDA        -3
+#define LS_ERR_NOMEM       -4
+#define LS_ERR_NCCL        -5
+#define LS_ERR_CALLBACK    -6
+
+#define LS_MEM_HOST   0
+#define LS_MEM_DEVICE 1
+
+/* FastM.quadRule, FastConvolution.jl:22-26 */
+#define LS_QUAD_TRAPEZOIDAL    0
+#define LS_QUAD_GREENGARD_VICO 1
+
+/* which reference method an apply reproduces */
+#define LS_APPLY_FASTCONVOLUTION 0   /* fastconvolution(M,b) = M*b, FastConvolution.jl:58-107; FastM3D `*`, FastConvolution3D.jl:31-37 */
+#define LS_APPLY_FFTCONVOLUTION  1   /* FFTconvolution(M,b), FastConvolution.jl:110-154; FastConvolution3D.jl:39-63 */
+
+/* ---- library ------------------------------------------------------------------------ */
+int         ls_version(void);
+const char* ls_last_error(void);
+int         ls_device_count(int* count);
+int         ls_set_device(int device);          /* one process per GPU: call with LOCAL_RANK first */
+
+/* ---- raw device buffers (for callers that keep Krylov vectors resident) --------------- */
+int ls_dev_alloc(void** dptr, size_t bytes);
+int ls_dev_free(void* dptr);
+int ls_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+int ls_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+int ls_host_alloc_pinned(void** hptr, size_t bytes);
+int ls_host_free_pinned(void* hptr);
+
+/* ---- 2-D operator: struct FastM, FastConvolution.jl:11-27 ----------------------------- *
+ * create copies nu (n*m doubles) and GFFT (ne*me complex, column-major, the reference's
+ * centred ordering for Greengard_Vico - the fftshift/ifftshift pair of FastConvolution.jl:94,98
+ * is folded into a one-time permutation) to the device.  Nothing of the caller's memory is
+ * kept.  Served on the GPU fast path: Greengard_Vico with ne = 4n, me = 4m and n, m in
+ * {64,...,4096} powers of two.                                                           */
+int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
+                   const double* nu, const ls_cdouble* gfft, double omega,
+                   int quadrule, int flags);
+/* y = M*b (mode 0; `*` FastConvolution.jl:43-48, mul! :50-54) or FFTconvolution(M,b) (mode 1).
+ * b and y hold n*m complex values and may alias.                                          */
+int ls_op2d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc);
+/* size(M,dim) / eltype, FastConvolution.jl:31-41: writes N = n*m */
+int ls_op_size(ls_handle h, int64_t* N);
+
+/* ---- handle services ------------------------------------------------------------------ */
+int ls_destroy(ls_handle h);
+int ls_sync(ls_handle h);
+/* CUDA-event timer on the handle's own stream (the stream its kernels are launched on) */
+int ls_timer_start(ls_handle h);
+int ls_timer_stop(ls_handle h, float* elapsed_ms);
+/* number of kernels this handle has launched since creation (bench `gpu_launches`) */
+int ls_launch_count(ls_handle h, int64_t* count);
+
+/* ---- test hooks ----------------------------------------------------------------------- */
+/* batched forward DFT (natural order out) / round trip of `nlines` lines of length N through
+ * the line-FFT engine; device-side unit test of fft_engine.cuh.                           */
+int ls_test_fft_lines(int64_t N, int64_t nlines, const ls_cdouble* in_host, ls_cdouble* out_host,
+                      int inverse_roundtrip);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS_CUDA_H */

@@ -1,0 +1,99 @@
+"""GPU parity of the 2-D operator apply against the CPU oracle (through the C ABI).
+
+Tolerance: relative L2 error <= 1e-12 per apply (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def _problem(n, m=None):
+    from oracle import ls_oracle as O
+    m = n if m is None else m
+    h = 1.0 / n
+    x = -0.5 + h * np.arange(n)
+    y = -0.5 * m / n + h * np.arange(m)
+    k = 2 * np.pi / (10 * h)
+    return O.buildFastConvolution(x, y, h, k, O.nu_gaussian_2d, quadRule="Greengard_Vico")
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024])
+def test_fastconvolution_matches_oracle(n):
+    from oracle import ls_oracle as O
+    import fast_solver_lippmann_schwinger_b200 as ls
+    Mo = _problem(n)
+    Mg = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.n, Mo.m, Mo.omega, quadRule="Greengard_Vico")
+    rng = np.random.default_rng(1234)
+    b = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    y_ref = O.fastconvolution(Mo, b)
+    y = Mg * b
+    assert _rel(y, y_ref) <= TOL
+    # the identity part must not hide the convolution: compare the convolution alone
+    assert _rel(y - b, y_ref - b) <= 1e-11
+    # plane wave (example.jl:76)
+    X, _ = O.grid2d(-0.5 + np.arange(n) / n, -0.5 + np.arange(n) / n)
+    u = np.exp(1j * Mo.omega * X)
+    assert _rel(Mg * u, O.fastconvolution(Mo, u)) <= TOL
+    # mul! into a preallocated vector, and FFTconvolution (Q2: no nu, no omega^2)
+    Y = np.zeros(n * n, dtype=np.complex128)
+    Mg.mul_(Y, b)
+    assert np.array_equal(Y, y)
+    assert _rel(ls.FFTconvolution(Mg, b), O.FFTconvolution(Mo, b)) <= TOL
+
+
+@pytest.mark.parametrize("n,m", [(64, 256), (256, 128), (512, 64)])
+def test_rectangular_grid(n, m):
+    from oracle import ls_oracle as O
+    import fast_solver_lippmann_schwinger_b200 as ls
+    Mo = _problem(n, m)
+    Mg = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.n, Mo.m, Mo.omega, quadRule="Greengard_Vico")
+    rng = np.random.default_rng(7)
+    b = rng.standard_normal(n * m) + 1j * rng.standard_normal(n * m)
+    assert _rel(Mg * b, O.fastconvolution(Mo, b)) <= TOL
+    with pytest.raises(ls.LSCudaError):
+        ls.FFTconvolution(Mg, b)          # Q3: square grids only
+
+
+def test_linearity_and_device_buffers():
+    import fast_solver_lippmann_schwinger_b200 as ls
+    n = 256
+    Mo = _problem(n)
+    Mg = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.n, Mo.m, Mo.omega, quadRule="Greengard_Vico")
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    b = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    al = 0.3 - 1.7j
+    lhs = Mg * (a + al * b)
+    rhs = Mg * a + al * (Mg * b)
+    assert _rel(lhs, rhs) <= 1e-13
+    db = ls.DeviceBuffer.from_host(a)
+    dy = ls.DeviceBuffer(a.nbytes)
+    Mg.mul_(dy, db)
+    Mg.sync()
+    assert np.array_equal(dy.to_host(), Mg * a)
+    # in place (y aliases b)
+    Mg.mul_(db, db)
+    Mg.sync()
+    assert np.array_equal(db.to_host(), Mg * a)
+
+
+def test_unsupported_and_invalid_inputs():
+    import fast_solver_lippmann_schwinger_b200 as ls
+    g = np.zeros((41, 41), dtype=np.complex128)
+    with pytest.raises(ls.LSUnsupported):
+        ls.FastM(g, np.zeros(21 * 21), 41, 41, 21, 21, 20.0)           # trapezoidal: not on the GPU path yet
+    M = ls.FastM(np.zeros((256, 256), complex), np.zeros(64 * 64), 256, 256, 64, 64, 1.0, quadRule="Greengard_Vico")
+    with pytest.raises(ValueError):
+        M * np.zeros(5, complex)                                       # DimensionMismatch
+    with pytest.raises(TypeError):
+        M * np.zeros(64 * 64)                                          # MethodError upstream: not Complex{Float64}
+    with pytest.raises(ls.LSCudaError):
+        M._apply(np.zeros(64 * 64, complex), None, 7)                  # unknown mode
+    with pytest.raises(ValueError):
+        ls.FastM(np.zeros((256, 255), complex), np.zeros(64 * 64), 256, 256, 64, 64, 1.0, quadRule="Greengard_Vico")
