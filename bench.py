@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py - LS operator applies/s on B200 (driver contract, see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 2048]
+
+Workload at every N: BASELINE.json configs[1] at its headline size - the 2-D Greengard-Vico
+Lippmann-Schwinger operator apply on a 2048 x 2048 grid (padded 8192 x 8192), 10 points per
+wavelength, Gaussian-bump contrast, complex128, one apply per step.  2-D grids run on one GPU
+("replicas only"), so for N > 1 every rank applies its own replica and
+`value` is the sum (weak scaling, no data-path collective).
+
+`value`  : applies/s with b and y resident in HBM (CUDA events on the handle's stream).
+`e2e`    : the same apply through the public host API (`FastM * b` on host arrays) with the
+           host->device copy of b from pinned memory and the device->host copy of y inside
+           the timed region.
+`roofline`: the dominant kernel (P2, k_mid_fused) - algorithmic bytes 384*N per launch over
+           its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline`: the oracle's literal restatement of fastconvolution (scipy.fft, all host
+           cores) on the same workload, a bounded sample of applies.
+`--impl reference` times that CPU path alone (the reference is Julia; Julia/FFTW are not in
+           this image, so the oracle port is the reference arm - see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ls_operator_applies_per_s_2d"
+UNIT = "applies/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_apply_rate(n, min_seconds=10.0, max_applies=8):
+    """Times the oracle's literal fastconvolution (FastConvolution.jl:84-106 restated) on the
+    host cores.  Returns (applies/s, cores, n_applies)."""
+    from oracle import ls_oracle as O
+    from fast_solver_lippmann_schwinger_b200.problems import gv_problem_2d
+    nu, gfft, k, h = gv_problem_2d(n)
+    M = O.FastM(gfft, nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico")
+    rng = np.random.default_rng(1234)
+    b = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    O.fastconvolution(M, b)                       # warm-up (pocketfft plan cache, page faults)
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_applies and (len(times) < 2 or time.perf_counter() - t_all < min_seconds):
+        t0 = time.perf_counter()
+        O.fastconvolution(M, b)
+        times.append(time.perf_counter() - t0)
+    return 1.0 / min(times), O.WORKERS, len(times)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import ls_oracle as O
+    from fast_solver_lippmann_schwinger_b200.problems import gv_problem_2d
+    n = args.n
+    nu, gfft, k, h = gv_problem_2d(n)
+    M = O.FastM(gfft, nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico")
+    rng = np.random.default_rng(1234)
+    b = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    for _ in range(args.warmup):
+        O.fastconvolution(M, b)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.fastconvolution(M, b)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)",
+        "data": "synthetic",
+        "config": workload_config(n),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.WORKERS, "kind": "port",
+                         "sample": "%d full applies of the %dx%d workload (oracle restatement of "
+                                   "FastConvolution.jl:84-106, scipy.fft pocketfft; Julia/FFTW absent)" % (args.steps, n, n)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "2-D Greengard_Vico LS operator apply, grid %dx%d (padded %dx%d), k=2pi/(10h), "
+                        "Gaussian-bump contrast (examples/example.jl:48), rng(1234) complex input" % (n, n, 4 * n, 4 * n),
+            "grid": [n, n], "padded": [4 * n, 4 * n], "quadRule": "Greengard_Vico", "points_per_wavelength": 10,
+            "l2_policy": "inputs larger than L2 (spectrum %.2f GB, intermediates %.2f GB each per apply)" % (
+                16 * 16 * n * n / 1e9, 64 * n * n / 1e9),
+            "parallelism": "replica per GPU (2-D path does not shard)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20      # bounded sample: ~1-2 s of 8-core CPU work per apply at 2048^2
+        run_reference(args, rank, world)
+        return
+
+    args.warmup = max(args.warmup, 3)
+    import fast_solver_lippmann_schwinger_b200 as ls
+    from fast_solver_lippmann_schwinger_b200._lib import check, lib
+    from fast_solver_lippmann_schwinger_b200.problems import gv_problem_2d
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    check(lib().ls_set_device(local_rank))
+
+    n = args.n
+    N = n * n
+    nu, gfft, k, h = gv_problem_2d(n)
+    M = ls.FastM(gfft, nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico")
+    del gfft
+    rng = np.random.default_rng(1234 + rank)
+    b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    db = ls.DeviceBuffer.from_host(b)
+    dy = ls.DeviceBuffer(b.nbytes)
+
+    def barrier():
+        M.sync()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    # ---- device-resident timed region -------------------------------------------------
+    for _ in range(args.warmup):
+        M.mul_(dy, db)
+    barrier()
+    launches0 = M.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    M.profile_enable(True)
+    barrier()
+    M.timer_start()
+    for _ in range(args.steps):
+        M.mul_(dy, db)
+    ms = M.timer_stop()
+    barrier()
+    phase_ms, phase_cnt = M.profile_read(3)
+    M.profile_enable(False)
+    launches = M.launch_count() - launches0
+
+    # ---- end to end through the public host API (pinned host buffers) -----------------------
+    hb = ls.PinnedArray((N,))
+    hy = ls.PinnedArray((N,))
+    hb.array[:] = b
+    e2e_steps = max(5, min(args.steps, 20))
+    for _ in range(2):
+        ls.fastconvolution(M, hb.array, out=hy.array)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ls.fastconvolution(M, hb.array, out=hy.array)    # H2D b, 3 kernels, D2H y, synchronous
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    checksum = float(np.abs(hy.array).sum())
+
+    # ---- max over ranks ---------------------------------------------------------------
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = world * args.steps / (ms * 1e-3)
+        p2_ms = phase_ms[1] / max(phase_cnt[1], 1)
+        alg_bytes_p2 = 384.0 * N          # A read 64N + spectrum 256N + C write 64N
+        achieved = alg_bytes_p2 / (p2_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+            "config": workload_config(n),
+            "e2e": {"value": world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N,
+                    "d2h_bytes_per_step": 16 * N, "steps": e2e_steps, "api": "fastconvolution(FastM, b) on pinned host arrays"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: 4x forward FFT, spectrum multiply, inverse FFT per padded row)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_p2,
+                         "launch_ms": p2_ms},
+            "apply_roofline": {"algorithmic_bytes_per_apply": 568.0 * N, "achieved": 568.0 * N / (ms / args.steps * 1e-3) / 1e9,
+                               "frac": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs":
+                                   568.0 * N / (ms / args.steps * 1e-3) / 1e9 / 8000.0},
+            "phase_ms": {"P1_fwd_columns": phase_ms[0] / max(phase_cnt[0], 1), "P2_fused_rows": p2_ms,
+                         "P3_inv_columns": phase_ms[2] / max(phase_cnt[2], 1)},
+            "checksum": checksum,
+        }
+        if not args.no_cpu_baseline:
+            v, cores, napp = cpu_reference_apply_rate(n)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "best of %d full applies of the same %dx%d workload (oracle restatement of "
+                                              "FastConvolution.jl:84-106 on scipy.fft; Julia/FFTW absent)" % (napp, n, n)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

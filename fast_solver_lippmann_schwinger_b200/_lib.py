@@ -75,6 +75,8 @@ def lib():
         "ls_timer_start": (ci, [vp]),
         "ls_timer_stop": (ci, [vp, C.POINTER(C.c_float)]),
         "ls_launch_count": (ci, [vp, C.POINTER(i64)]),
+        "ls_profile_enable": (ci, [vp, ci]),
+        "ls_profile_read": (ci, [vp, C.POINTER(dbl), C.POINTER(i64), ci]),
         "ls_test_fft_lines": (ci, [i64, i64, vp, vp, ci]),
     }
     for name, (res, args) in sig.items():

@@ -168,6 +168,29 @@ int ls_timer_stop(ls_handle h, float* ms) {
     return LS_OK;
 }
 
+int ls_profile_enable(ls_handle h, int on) {
+    LS_REQUIRE(h, LS_ERR_INVALID, "ls_profile_enable: null handle");
+    HandleBase* b = reinterpret_cast<HandleBase*>(h);
+    LS_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    for (auto& pe : b->phase_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    b->phase_events.clear();
+    b->profiling = on != 0;
+    return LS_OK;
+}
+
+int ls_profile_read(ls_handle h, double* ms, int64_t* counts, int nphase) {
+    LS_REQUIRE(h && ms && counts && nphase > 0, LS_ERR_INVALID, "ls_profile_read: bad argument");
+    HandleBase* b = reinterpret_cast<HandleBase*>(h);
+    LS_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < nphase; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (auto& pe : b->phase_events) {
+        float t = 0.f;
+        LS_CUDA_TRY(cudaEventElapsedTime(&t, pe.a, pe.b));
+        if (pe.phase >= 0 && pe.phase < nphase) { ms[pe.phase] += t; counts[pe.phase]++; }
+    }
+    return LS_OK;
+}
+
 int ls_op_size(ls_handle h, int64_t* N) {
     LS_REQUIRE(h && N, LS_ERR_INVALID, "ls_op_size: null argument");
     int64_t v = reinterpret_cast<HandleBase*>(h)->op_size();

@@ -48,6 +48,22 @@ struct HandleBase {
 
     virtual int64_t op_size() const { return -1; }
 
+    // optional per-phase CUDA-event profiling (bench roofline of the dominant kernel)
+    bool profiling = false;
+    struct PhaseEv { int phase; cudaEvent_t a, b; };
+    std::vector<PhaseEv> phase_events;
+    void phase_begin(int phase) {
+        if (!profiling) return;
+        PhaseEv pe; pe.phase = phase;
+        cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
+        cudaEventRecord(pe.a, stream);
+        phase_events.push_back(pe);
+    }
+    void phase_end() {
+        if (!profiling) return;
+        cudaEventRecord(phase_events.back().b, stream);
+    }
+
     int init_base(uint32_t k) {
         kind = k;
         LS_CUDA_TRY(cudaGetDevice(&device));
@@ -81,6 +97,7 @@ struct HandleBase {
     }
     virtual ~HandleBase() {
         if (stream) cudaStreamSynchronize(stream);
+        for (auto& pe : phase_events) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
         for (void* p : dev_allocs) cudaFree(p);
         for (void* p : host_allocs) cudaFreeHost(p);
         if (ev0) cudaEventDestroy(ev0);

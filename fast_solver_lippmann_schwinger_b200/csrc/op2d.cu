@@ -52,8 +52,10 @@ template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
         attr = true;
     }
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
+    op->phase_begin(0);
     k_fwd_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
         b, nu, op->d_A, op->d_Wn, op->d_MODn, op->n, 1, op->ne, 1, 0);
+    op->phase_end();
     op->launches++;
     return LS_OK;
 }
@@ -66,8 +68,10 @@ template <int N> int launch_mid(Op2D* op) {
     }
     dim3 grid((unsigned)(op->ne / GeoA<N>::LPC));
     // line = x slot sx; point j at A[sx + ne*j]; output line contiguous C[j + m*sx]
+    op->phase_begin(1);
     k_mid_fused<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
         op->d_A, op->d_C, op->d_G, op->d_Wm, op->d_MODm, 1, op->ne, op->m, 1, 0);
+    op->phase_end();
     op->launches++;
     return LS_OK;
 }
@@ -80,8 +84,10 @@ template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
     }
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
     // line = column j; slot sx at C[j + m*sx]
+    op->phase_begin(2);
     k_inv_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
         op->d_C, bsrc, y, op->d_Wn, op->d_MODn, scale, 1, op->m, op->n, 1, 0);
+    op->phase_end();
     op->launches++;
     return LS_OK;
 }

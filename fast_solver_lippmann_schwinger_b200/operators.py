@@ -61,6 +61,15 @@ class _Handle:
         check(lib().ls_timer_stop(self.handle, C.byref(ms)))
         return float(ms.value)
 
+    def profile_enable(self, on=True):
+        check(lib().ls_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self, nphase=8):
+        ms = (C.c_double * nphase)()
+        cnt = (C.c_int64 * nphase)()
+        check(lib().ls_profile_read(self.handle, ms, cnt, nphase))
+        return [float(x) for x in ms], [int(x) for x in cnt]
+
     def launch_count(self):
         c = C.c_int64()
         check(lib().ls_launch_count(self.handle, C.byref(c)))

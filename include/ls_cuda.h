@@ -86,6 +86,12 @@ int ls_timer_stop(ls_handle h, float* elapsed_ms);
 /* number of kernels this handle has launched since creation (bench `gpu_launches`) */
 int ls_launch_count(ls_handle h, int64_t* count);
 
+/* per-phase CUDA-event profile of the handle's launches (phase ids are listed per operator
+ * in DESIGN.md; 2-D: 0 = P1 forward columns, 1 = P2 fused rows, 2 = P3 inverse columns).
+ * ls_profile_read synchronises and returns cumulative milliseconds and launch counts.     */
+int ls_profile_enable(ls_handle h, int on);
+int ls_profile_read(ls_handle h, double* ms_per_phase, int64_t* launches_per_phase, int nphase);
+
 /* ---- test hooks ----------------------------------------------------------------------- */
 /* batched forward DFT (natural order out) / round trip of `nlines` lines of length N through
  * the line-FFT engine; device-side unit test of fft_engine.cuh.                           */
