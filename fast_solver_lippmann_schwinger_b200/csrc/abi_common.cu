@@ -71,6 +71,30 @@ std::vector<cd> modulation_table(long N) {
     return w;
 }
 
+std::vector<cd> engine_table(int N) {
+    int E, S, R0, R1;
+    switch (N) {
+        case 64:   E = 8;  S = 2; R0 = 8;  R1 = 8;  break;
+        case 128:  E = 16; S = 2; R0 = 16; R1 = 8;  break;
+        case 256:  E = 16; S = 2; R0 = 16; R1 = 16; break;
+        case 512:  E = 8;  S = 3; R0 = 8;  R1 = 8;  break;
+        case 1024: E = 16; S = 3; R0 = 16; R1 = 8;  break;
+        case 2048: E = 16; S = 3; R0 = 16; R1 = 16; break;
+        case 4096: E = 16; S = 3; R0 = 16; R1 = 16; break;
+        default: return std::vector<cd>();
+    }
+    const int T = N / E;
+    std::vector<cd> tab;
+    for (int t = 0; t < T; ++t) tab.push_back(unit_root(t, 4L * N));
+    for (int t = 0; t < T; ++t) tab.push_back(unit_root(t, N));
+    if (S == 3) {
+        const int Mprev = N / R0, M = Mprev / R1;
+        for (int d = 0; d < R1; ++d)
+            for (int b = 0; b < M; ++b) tab.push_back(unit_root((long)b * d, Mprev));
+    }
+    return tab;
+}
+
 int upload(void** dptr, const void* host, size_t bytes, cudaStream_t s) {
     LS_CUDA_TRY(cudaMalloc(dptr, bytes));
     LS_CUDA_TRY(cudaMemcpyAsync(*dptr, host, bytes, cudaMemcpyHostToDevice, s));

@@ -15,6 +15,7 @@
 // XOR swizzle below (128-bit accesses are served per quarter warp = 8 lanes).
 #pragma once
 #include <cuda_runtime.h>
+#include "w64_table.cuh"
 
 namespace lsfft {
 
@@ -205,9 +206,107 @@ __device__ __forceinline__ void ld_stage(cd* v, int t, const cd* sm, const Lay& 
         for (int a = 0; a < St::R; ++a) v[u * St::R + a] = sm[lay.phys(St::addr(t, u, a))];
 }
 
-// butterflies (+ DIF twiddles) of stage I, forward
+// ------------------------------------------------------------------------------------
+// Twiddles.  No per-point table lookups on the hot path:
+//  * stage 0 carries the pruned-FFT modulation with it.  For sub-transform r (0..3) of a line
+//    zero-padded to 4N the input is x[j] * w_{4N}^{r j}, j = a*T + t.  The a-dependent part
+//    w_{4E}^{r a} is a warp-uniform constant (constant bank); the t-dependent part merges
+//    with the DIF twiddle w_N^{t d} into q^(4d + r), q = w_{4N}^t, generated from two
+//    per-thread constants (q, s = q^4) by a short product recurrence in registers.
+//  * middle stages (3-stage sizes only) read a tiny [d][b] table staged in shared memory.
+// ------------------------------------------------------------------------------------
+template <int N> struct TwState {
+    cd q;            // w_{4N}^t
+    cd s;            // w_N^t  (= q^4, taken from the table for accuracy)
+    cd s2;           // s^2
+    const cd* tw1;   // shared-memory table of stage 1, entry [d*M1 + b] = w_{Mprev1}^{b d}
+};
+
+// engine table for size N (built on the host, ls::engine_table):
+//   [0, T)            q_t = exp(-2 pi i t/(4N))
+//   [T, 2T)           s_t = exp(-2 pi i t/N)
+//   [2T, 2T + TW1N)   stage-1 table (3-stage sizes), TW1N = N/R0
+template <int N> struct EngTab {
+    static constexpr int T = N / Cfg<N>::E;
+    static constexpr int TW1N = (Cfg<N>::S == 3) ? N / Cfg<N>::R0 : 0;
+    static constexpr int TOTAL = 2 * T + TW1N;
+};
+
+// cooperative copy of the stage-1 table into shared memory (call before the first sync)
+template <int N>
+__device__ __forceinline__ void load_tw1(cd* tw1_sm, const cd* __restrict__ tab) {
+    for (int i = threadIdx.x; i < EngTab<N>::TW1N; i += blockDim.x) tw1_sm[i] = tab[2 * EngTab<N>::T + i];
+}
+template <int N>
+__device__ __forceinline__ TwState<N> make_tw(int t, const cd* __restrict__ tab, const cd* tw1_sm) {
+    TwState<N> tw;
+    tw.q = tab[t];
+    tw.s = tab[EngTab<N>::T + t];
+    tw.s2 = cmul(tw.s, tw.s);
+    tw.tw1 = tw1_sm;
+    return tw;
+}
+
+__device__ __forceinline__ cd c64(int k) { return make_double2(C64_RE[k & 63], C64_IM[k & 63]); }
+
+// v[d] *= q^(4d + r)  (CONJ: by the conjugate), d = 0..E-1; two interleaved product chains
+template <int N, bool CONJ>
+__device__ __forceinline__ void mul_stage0_twiddles(cd* v, int r, const TwState<N>& tw) {
+    constexpr int E = Cfg<N>::E;
+    cd pe;   // q^r
+    if (r == 0) pe = make_double2(1.0, 0.0);
+    else if (r == 1) pe = tw.q;
+    else {
+        cd q2 = cmul(tw.q, tw.q);
+        pe = (r == 2) ? q2 : cmul(q2, tw.q);
+    }
+    cd po = cmul(pe, tw.s);
+    if (r != 0) v[0] = CONJ ? cmulc(v[0], pe) : cmul(v[0], pe);
+    v[1] = CONJ ? cmulc(v[1], po) : cmul(v[1], po);
+#pragma unroll
+    for (int d = 2; d < E; d += 2) {
+        pe = cmul(pe, tw.s2);
+        po = cmul(po, tw.s2);
+        v[d] = CONJ ? cmulc(v[d], pe) : cmul(v[d], pe);
+        v[d + 1] = CONJ ? cmulc(v[d + 1], po) : cmul(v[d + 1], po);
+    }
+}
+
+// stage 0, forward, sub-transform r:  in v[a] = x[a*T + t] (unmodulated)
+template <int N>
+__device__ __forceinline__ void fwd_stage0(cd* v, int r, const TwState<N>& tw) {
+    constexpr int E = Cfg<N>::E;
+    if (r != 0) {
+#pragma unroll
+        for (int a = 1; a < E; ++a) v[a] = cmul(v[a], c64(r * a * (16 / E)));
+    }
+    dftR<-1, E>(v);
+    mul_stage0_twiddles<N, false>(v, r, tw);
+}
+// adjoint of fwd_stage0 without the final demodulation constants: out v[a] = sum_d ...;
+// the caller accumulates acc[a] += v[a] * conj(c64(r a 16/E)).
+template <int N>
+__device__ __forceinline__ void inv_stage0(cd* v, int r, const TwState<N>& tw) {
+    constexpr int E = Cfg<N>::E;
+    mul_stage0_twiddles<N, true>(v, r, tw);
+    dftR<+1, E>(v);
+}
+template <int N>
+__device__ __forceinline__ void demod_accumulate(cd* acc, const cd* v, int r) {
+    constexpr int E = Cfg<N>::E;
+    if (r == 0) {
+#pragma unroll
+        for (int a = 0; a < E; ++a) acc[a] = v[a];
+    } else {
+        acc[0] = cadd(acc[0], v[0]);
+#pragma unroll
+        for (int a = 1; a < E; ++a) acc[a] = cfmac(v[a], c64(r * a * (16 / E)), acc[a]);
+    }
+}
+
+// middle / last stages ------------------------------------------------------------------
 template <int N, int I>
-__device__ __forceinline__ void fwd_stage(cd* v, int t, const cd* __restrict__ W) {
+__device__ __forceinline__ void fwd_stage(cd* v, int t, const TwState<N>& tw) {
     typedef Stage<N, I> St;
 #pragma unroll
     for (int u = 0; u < St::NB; ++u) {
@@ -215,64 +314,90 @@ __device__ __forceinline__ void fwd_stage(cd* v, int t, const cd* __restrict__ W
         if (!St::LAST) {
             int b = St::bidx(t, u);
 #pragma unroll
-            for (int d = 1; d < St::R; ++d) {
-                cd w = __ldg(&W[(b * d) * (N / St::Mprev)]);
-                v[u * St::R + d] = cmul(v[u * St::R + d], w);
-            }
+            for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmul(v[u * St::R + d], tw.tw1[d * St::M + b]);
         }
     }
 }
-// adjoint of fwd_stage: conjugate twiddles, then inverse butterflies
 template <int N, int I>
-__device__ __forceinline__ void inv_stage(cd* v, int t, const cd* __restrict__ W) {
+__device__ __forceinline__ void inv_stage(cd* v, int t, const TwState<N>& tw) {
     typedef Stage<N, I> St;
 #pragma unroll
     for (int u = 0; u < St::NB; ++u) {
         if (!St::LAST) {
             int b = St::bidx(t, u);
 #pragma unroll
-            for (int d = 1; d < St::R; ++d) {
-                cd w = __ldg(&W[(b * d) * (N / St::Mprev)]);
-                v[u * St::R + d] = cmulc(v[u * St::R + d], w);
-            }
+            for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmulc(v[u * St::R + d], tw.tw1[d * St::M + b]);
         }
         dftR<+1, St::R>(v + u * St::R);
     }
 }
 
-// Forward FFT of one line.  In: v[a] = x[a*T + t].  Out: v[e] = X[freq(t + T*e)].
-// W = table exp(-2 pi i k/N), k < N.  sm/lay = this line's exchange buffer (N points).
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// Forward FFT of sub-transform r of one line.  In: v[a] = x[a*T + t].  Out: v[e] = X_r[freq(t + T*e)],
+// X_r = FFT_N(x[j] w_{4N}^{r j}).  sm/lay = this line's exchange buffer (N points).
 template <int N, class Lay>
-__device__ __forceinline__ void fft_fwd(cd* v, int t, cd* sm, const Lay& lay, const cd* __restrict__ W) {
+__device__ __forceinline__ void fft_fwd(cd* v, int t, int r, cd* sm, const Lay& lay, const TwState<N>& tw) {
     typedef Cfg<N> C;
-    fwd_stage<N, 0>(v, t, W);
+    fwd_stage0<N>(v, r, tw);
     st_stage<N, 0>(v, t, sm, lay);
     __syncthreads();
     ld_stage<N, 1>(v, t, sm, lay);
-    fwd_stage<N, 1>(v, t, W);
-    if (C::S == 3) {
+    fwd_stage<N, 1>(v, t, tw);
+    if constexpr (C::S == 3) {
         st_stage<N, 1>(v, t, sm, lay);
         __syncthreads();
         ld_stage<N, 2>(v, t, sm, lay);
-        fwd_stage<N, 2>(v, t, W);
+        fwd_stage<N, 2>(v, t, tw);
     }
 }
 
-// Unnormalised inverse FFT (adjoint network).  In: v[e] = X[freq(t + T*e)].  Out: v[a] = N*x[a*T + t].
-template <int N, class Lay>
-__device__ __forceinline__ void fft_inv(cd* v, int t, cd* sm, const Lay& lay, const cd* __restrict__ W) {
+// Adjoint network (unnormalised inverse) up to, not including, the demodulation constants.
+// In: v[e] = Y_r[freq(t + T*e)].  Out: v[a]; then y[a*T+t] += v[a]*conj(c64(..)) (demod_accumulate).
+// `hook` runs on every thread right after the first __syncthreads() of the inverse.
+template <int N, class Lay, class Hook = NoHook>
+__device__ __forceinline__ void fft_inv(cd* v, int t, int r, cd* sm, const Lay& lay, const TwState<N>& tw,
+                                        Hook hook = Hook()) {
     typedef Cfg<N> C;
-    if (C::S == 3) {
-        inv_stage<N, 2>(v, t, W);
+    if constexpr (C::S == 3) {
+        inv_stage<N, 2>(v, t, tw);
         st_stage<N, 2>(v, t, sm, lay);
         __syncthreads();
+        hook();
         ld_stage<N, 1>(v, t, sm, lay);
+        inv_stage<N, 1>(v, t, tw);
+        st_stage<N, 1>(v, t, sm, lay);
+        __syncthreads();
+    } else {
+        inv_stage<N, 1>(v, t, tw);
+        st_stage<N, 1>(v, t, sm, lay);
+        __syncthreads();
+        hook();
     }
-    inv_stage<N, 1>(v, t, W);
-    st_stage<N, 1>(v, t, sm, lay);
-    __syncthreads();
     ld_stage<N, 0>(v, t, sm, lay);
-    inv_stage<N, 0>(v, t, W);
+    inv_stage0<N>(v, r, tw);
 }
+
+// ---- TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX) -------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace lsfft

@@ -44,6 +44,7 @@ template <int N> struct Map<N, false> {
         t = threadIdx.x % G::T;
         lay.base = line * N;
     }
+    __device__ __forceinline__ int lay_lam() const { return 0; }
 };
 template <int N> struct Map<N, true> {
     typedef GeoB<N> G;
@@ -59,9 +60,18 @@ template <int N> struct Map<N, true> {
         smoff = grp * 8 * N;
     }
     int smoff;
+    __device__ __forceinline__ int lay_lam() const { return lay.lam; }
 };
 template <int N> __device__ __forceinline__ int sm_group_off(const Map<N, false>&) { return 0; }
 template <int N> __device__ __forceinline__ int sm_group_off(const Map<N, true>& m) { return m.smoff; }
+
+// per-CTA shared memory: [exchange: LPC*N][(mid only) x copy: LPC*N][(mid only) spectrum: LPC*N][tw1][mbarrier]
+template <int N, bool MODE_B> struct Smem {
+    static constexpr int LPC = MODE_B ? GeoB<N>::LPC : GeoA<N>::LPC;
+    static constexpr int TW1N = EngTab<N>::TW1N;
+    static constexpr int fwd_bytes = (LPC * N + TW1N) * (int)sizeof(cd);
+    static constexpr int mid_bytes = (3 * LPC * N + TW1N) * (int)sizeof(cd) + 16;
+};
 
 // ---- forward, pruned: N inputs -> 4N slots -------------------------------------------
 // in  : line L point j at in[L*in_ls + j*in_es], optionally scaled by the real nu (same addressing)
@@ -69,15 +79,18 @@ template <int N> __device__ __forceinline__ int sm_group_off(const Map<N, true>&
 template <int N, bool MODE_B>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
 k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __restrict__ out,
-             const cd* __restrict__ W, const cd* __restrict__ MOD,
+             const cd* __restrict__ TAB,
              long in_ls, long in_es, long out_ls, long out_es, long line0) {
     typedef Map<N, MODE_B> M;
-    constexpr int E = Cfg<N>::E, T = N / E;
-    extern __shared__ cd sm[];
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
+    extern __shared__ __align__(128) cd sm[];
     M mp;
     cd* ex = sm + sm_group_off(mp);
-    const long L = line0 + (long)blockIdx.x * M::G::LPC + mp.line;
+    cd* tw1 = sm + LPC * N;
+    load_tw1<N>(tw1, TAB);
+    const long L = line0 + (long)blockIdx.x * LPC + mp.line;
     const int t = mp.t;
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
     cd x[E];
 #pragma unroll
     for (int a = 0; a < E; ++a) {
@@ -90,17 +103,13 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
         }
         x[a] = val;
     }
+    __syncthreads();   // tw1 visible
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
         cd v[E];
-        if (r == 0) {
 #pragma unroll
-            for (int a = 0; a < E; ++a) v[a] = x[a];
-        } else {
-#pragma unroll
-            for (int a = 0; a < E; ++a) v[a] = cmul(x[a], __ldg(&MOD[(r - 1) * N + a * T + t]));
-        }
-        fft_fwd<N>(v, t, ex, mp.lay, W);
+        for (int a = 0; a < E; ++a) v[a] = x[a];
+        fft_fwd<N>(v, t, r, ex, mp.lay, tw);
         cd* o = out + L * out_ls + (long)(r * N + t) * out_es;
 #pragma unroll
         for (int e = 0; e < E; ++e) o[(long)(T * e) * out_es] = v[e];
@@ -112,60 +121,74 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
 // in  : line L point j at in[L*in_ls + j*in_es]
 // G   : spectrum of line L, block r, slot s at G[(L*4 + r)*N + s]                 (mode A)
 //       or at G[((L/8)*4 + r)*8N + s*8 + L%8]                                     (mode B)
+//       -> per (unit, r) one contiguous chunk, fetched by TMA bulk copy into shared memory
+//          while the previous block's inverse transform runs.
 // out : line L point j at out[L*out_ls + j*out_es]  (may alias in when strides agree)
 template <int N, bool MODE_B>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
-k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G,
-            const cd* __restrict__ W, const cd* __restrict__ MOD,
+k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB,
             long in_ls, long in_es, long out_ls, long out_es, long line0) {
     typedef Map<N, MODE_B> M;
-    constexpr int E = Cfg<N>::E, T = N / E;
-    extern __shared__ cd sm[];
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
+    constexpr int UNIT = MODE_B ? 8 * N : N;          // points per spectrum chunk
+    constexpr int UPC = LPC * N / UNIT;               // chunks per CTA and r
+    extern __shared__ __align__(128) cd sm[];
     M mp;
     cd* ex = sm + sm_group_off(mp);
-    cd* xs = sm + M::G::LPC * N + sm_group_off(mp);   // thread-private copy of the input line
-    const long L = line0 + (long)blockIdx.x * M::G::LPC + mp.line;
+    cd* xs = sm + LPC * N + sm_group_off(mp);   // thread-private copy of the input line
+    cd* gb = sm + 2 * LPC * N;                  // spectrum chunk(s) of the current r
+    cd* tw1 = sm + 3 * LPC * N;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tw1 + Smem<N, MODE_B>::TW1N);
+    const long Lcta = line0 + (long)blockIdx.x * LPC;
+    const long L = Lcta + mp.line;
     const int t = mp.t;
+    const cd* gsrc = G + (MODE_B ? (Lcta >> 3) : Lcta) * 4L * UNIT;   // chunk (unit u, r) at gsrc + (u*4 + r)*UNIT
+
+    auto issue_g = [&](int r) {
+        mbar_expect_tx(bar, (unsigned)(UPC * UNIT * sizeof(cd)));
+#pragma unroll
+        for (int u = 0; u < UPC; ++u)
+            bulk_g2s(gb + u * UNIT, gsrc + ((long)u * 4 + r) * UNIT, (unsigned)(UNIT * sizeof(cd)), bar);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_proxy_async();
+        issue_g(0);
+    }
+    load_tw1<N>(tw1, TAB);
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
     {
         const cd* p = in + L * in_ls + (long)t * in_es;
 #pragma unroll
         for (int a = 0; a < E; ++a) xs[mp.lay.phys(a * T + t)] = p[(long)(a * T) * in_es];
     }
+    __syncthreads();   // tw1 + mbarrier init visible
     cd acc[E];
-#pragma unroll
-    for (int a = 0; a < E; ++a) acc[a] = make_double2(0.0, 0.0);
-    const cd* g;
-    long gstep;
-    if (MODE_B) {
-        g = G + ((L >> 3) * 4) * (long)(8 * N) + (long)t * 8 + (L & 7);
-        gstep = 8;
-    } else {
-        g = G + (L * 4) * (long)N + t;
-        gstep = 1;
-    }
+    const int goff = MODE_B ? 0 : mp.line * N;     // mode B: lay.phys already interleaves the 8 lines
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
         cd v[E];
-        if (r == 0) {
 #pragma unroll
-            for (int a = 0; a < E; ++a) v[a] = xs[mp.lay.phys(a * T + t)];
+        for (int a = 0; a < E; ++a) v[a] = xs[mp.lay.phys(a * T + t)];
+        fft_fwd<N>(v, t, r, ex, mp.lay, tw);
+        mbar_wait(bar, (unsigned)(r & 1));
+        if (MODE_B) {
+            const cd* g = gb + sm_group_off(mp);
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], g[(t + T * e) * 8 + mp.lay_lam()]);
         } else {
+            const cd* g = gb + goff;
 #pragma unroll
-            for (int a = 0; a < E; ++a)
-                v[a] = cmul(xs[mp.lay.phys(a * T + t)], __ldg(&MOD[(r - 1) * N + a * T + t]));
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], g[t + T * e]);
         }
-        fft_fwd<N>(v, t, ex, mp.lay, W);
-        const cd* gr = g + (long)r * N * gstep;
-#pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], __ldg(&gr[(long)(T * e) * gstep]));
-        fft_inv<N>(v, t, ex, mp.lay, W);
-        if (r == 0) {
-#pragma unroll
-            for (int a = 0; a < E; ++a) acc[a] = v[a];
-        } else {
-#pragma unroll
-            for (int a = 0; a < E; ++a) acc[a] = cfmac(v[a], __ldg(&MOD[(r - 1) * N + a * T + t]), acc[a]);
-        }
+        fft_inv<N>(v, t, r, ex, mp.lay, tw, [&]() {
+            // every thread has consumed gb (the multiply precedes this barrier): refill it
+            if (r < 3 && threadIdx.x == 0) {
+                fence_proxy_async();
+                issue_g(r + 1);
+            }
+        });
+        demod_accumulate<N>(acc, v, r);
     }
     cd* o = out + L * out_ls + (long)t * out_es;
 #pragma unroll
@@ -177,16 +200,19 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G,
 // out : line L point j at out[L*out_ls + j*out_es];  if bsrc: out = bsrc + scale*result
 template <int N, bool MODE_B>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
-k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out,
-             const cd* __restrict__ W, const cd* __restrict__ MOD, double scale,
+k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __restrict__ TAB, double scale,
              long in_ls, long in_es, long out_ls, long out_es, long line0) {
     typedef Map<N, MODE_B> M;
-    constexpr int E = Cfg<N>::E, T = N / E;
-    extern __shared__ cd sm[];
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
+    extern __shared__ __align__(128) cd sm[];
     M mp;
     cd* ex = sm + sm_group_off(mp);
-    const long L = line0 + (long)blockIdx.x * M::G::LPC + mp.line;
+    cd* tw1 = sm + LPC * N;
+    load_tw1<N>(tw1, TAB);
+    const long L = line0 + (long)blockIdx.x * LPC + mp.line;
     const int t = mp.t;
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    __syncthreads();
     cd acc[E];
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
@@ -194,14 +220,8 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out,
         const cd* p = in + L * in_ls + (long)(r * N + t) * in_es;
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = p[(long)(T * e) * in_es];
-        fft_inv<N>(v, t, ex, mp.lay, W);
-        if (r == 0) {
-#pragma unroll
-            for (int a = 0; a < E; ++a) acc[a] = v[a];
-        } else {
-#pragma unroll
-            for (int a = 0; a < E; ++a) acc[a] = cfmac(v[a], __ldg(&MOD[(r - 1) * N + a * T + t]), acc[a]);
-        }
+        fft_inv<N>(v, t, r, ex, mp.lay, tw);
+        demod_accumulate<N>(acc, v, r);
         __syncthreads();
     }
 #pragma unroll
@@ -212,10 +232,5 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out,
         out[off] = res;
     }
 }
-
-template <int N, bool MODE_B> constexpr int smem_fwd() {
-    return (MODE_B ? GeoB<N>::LPC : GeoA<N>::LPC) * N * (int)sizeof(cd);
-}
-template <int N, bool MODE_B> constexpr int smem_mid() { return 2 * smem_fwd<N, MODE_B>(); }
 
 }  // namespace lsk

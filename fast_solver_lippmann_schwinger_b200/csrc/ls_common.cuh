@@ -117,6 +117,9 @@ std::vector<cd> twiddle_table(long N, long count);
 // modulation table: mod[(r-1)*N + j] = exp(-2 pi i r j / (4N)), r = 1..3
 std::vector<cd> modulation_table(long N);
 
+// per-size engine table (fft_engine.cuh EngTab): q_t, s_t, stage-1 twiddles
+std::vector<cd> engine_table(int N);
+
 int upload(void** dptr, const void* host, size_t bytes, cudaStream_t s);
 
 }  // namespace ls

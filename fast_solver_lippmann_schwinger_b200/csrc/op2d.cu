@@ -19,8 +19,7 @@ struct Op2D : HandleBase {
     int quadrule = 0;
     double* d_nu = nullptr;
     cd* d_G = nullptr;        // [sx][ry][slot_y], scaled by 1/(ne*me)
-    cd* d_Wn = nullptr; cd* d_Wm = nullptr;
-    cd* d_MODn = nullptr; cd* d_MODm = nullptr;
+    cd* d_TABn = nullptr; cd* d_TABm = nullptr;   // engine tables (fft_engine.cuh EngTab)
     cd* d_A = nullptr;        // ne x m
     cd* d_C = nullptr;        // m x ne (line contiguous)
     cd* d_b = nullptr; cd* d_y = nullptr;   // staging for host-pointer applies
@@ -45,7 +44,7 @@ __global__ void k_permute_g2d(const cd* __restrict__ gin, cd* __restrict__ gout,
 }
 
 template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
-    constexpr int smem = smem_fwd<N, false>();
+    constexpr int smem = Smem<N, false>::fwd_bytes;
     static bool attr = false;
     if (!attr) {
         LS_CUDA_TRY(cudaFuncSetAttribute(k_fwd_pruned<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -54,13 +53,13 @@ template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
     op->phase_begin(0);
     k_fwd_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        b, nu, op->d_A, op->d_Wn, op->d_MODn, op->n, 1, op->ne, 1, 0);
+        b, nu, op->d_A, op->d_TABn, op->n, 1, op->ne, 1, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
 }
 template <int N> int launch_mid(Op2D* op) {
-    constexpr int smem = smem_mid<N, false>();
+    constexpr int smem = Smem<N, false>::mid_bytes;
     static bool attr = false;
     if (!attr) {
         LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -70,13 +69,13 @@ template <int N> int launch_mid(Op2D* op) {
     // line = x slot sx; point j at A[sx + ne*j]; output line contiguous C[j + m*sx]
     op->phase_begin(1);
     k_mid_fused<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        op->d_A, op->d_C, op->d_G, op->d_Wm, op->d_MODm, 1, op->ne, op->m, 1, 0);
+        op->d_A, op->d_C, op->d_G, op->d_TABm, 1, op->ne, op->m, 1, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
 }
 template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
-    constexpr int smem = smem_fwd<N, false>();
+    constexpr int smem = Smem<N, false>::fwd_bytes;
     static bool attr = false;
     if (!attr) {
         LS_CUDA_TRY(cudaFuncSetAttribute(k_inv_pruned<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -86,7 +85,7 @@ template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
     // line = column j; slot sx at C[j + m*sx]
     op->phase_begin(2);
     k_inv_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        op->d_C, bsrc, y, op->d_Wn, op->d_MODn, scale, 1, op->m, op->n, 1, 0);
+        op->d_C, bsrc, y, op->d_TABn, scale, 1, op->m, op->n, 1, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
@@ -152,12 +151,9 @@ int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
 #define TRY(x) do { rc = (x); if (rc) { delete op; return rc; } } while (0)
     TRY(op->dupload((void**)&op->d_nu, nu, N * sizeof(double)));
     {
-        auto Wn = twiddle_table(n, n), Wm = twiddle_table(m, m);
-        auto Mn = modulation_table(n), Mm = modulation_table(m);
-        TRY(op->dupload((void**)&op->d_Wn, Wn.data(), Wn.size() * sizeof(cd)));
-        TRY(op->dupload((void**)&op->d_Wm, Wm.data(), Wm.size() * sizeof(cd)));
-        TRY(op->dupload((void**)&op->d_MODn, Mn.data(), Mn.size() * sizeof(cd)));
-        TRY(op->dupload((void**)&op->d_MODm, Mm.data(), Mm.size() * sizeof(cd)));
+        auto Tn = engine_table((int)n), Tm = engine_table((int)m);
+        TRY(op->dupload((void**)&op->d_TABn, Tn.data(), Tn.size() * sizeof(cd)));
+        TRY(op->dupload((void**)&op->d_TABm, Tm.data(), Tm.size() * sizeof(cd)));
     }
     {
         // one-time permutation of the spectrum into [x slot][ry][y slot] order, ifftshift folded in

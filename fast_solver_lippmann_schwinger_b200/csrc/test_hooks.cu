@@ -10,18 +10,22 @@ namespace {
 
 template <int N>
 __global__ void __launch_bounds__(GeoA<N>::THREADS)
-k_test_fft(const cd* __restrict__ in, cd* __restrict__ out, const cd* __restrict__ W, int roundtrip) {
+k_test_fft(const cd* __restrict__ in, cd* __restrict__ out, const cd* __restrict__ TAB, int roundtrip) {
     constexpr int E = Cfg<N>::E, T = N / E;
-    extern __shared__ cd sm[];
+    extern __shared__ __align__(128) cd sm[];
     Map<N, false> mp;
+    cd* tw1 = sm + GeoA<N>::LPC * N;
+    load_tw1<N>(tw1, TAB);
     const long L = (long)blockIdx.x * GeoA<N>::LPC + mp.line;
     const int t = mp.t;
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    __syncthreads();
     cd v[E];
 #pragma unroll
     for (int a = 0; a < E; ++a) v[a] = in[L * N + a * T + t];
-    fft_fwd<N>(v, t, sm, mp.lay, W);
+    fft_fwd<N>(v, t, 0, sm, mp.lay, tw);
     if (roundtrip) {
-        fft_inv<N>(v, t, sm, mp.lay, W);
+        fft_inv<N>(v, t, 0, sm, mp.lay, tw);
 #pragma unroll
         for (int a = 0; a < E; ++a) out[L * N + a * T + t] = cscale(v[a], 1.0 / N);
     } else {
@@ -31,7 +35,7 @@ k_test_fft(const cd* __restrict__ in, cd* __restrict__ out, const cd* __restrict
 }
 
 template <int N> int run_test(long nlines, const cd* d_in, cd* d_out, const cd* d_W, int roundtrip) {
-    constexpr int smem = smem_fwd<N, false>();
+    constexpr int smem = Smem<N, false>::fwd_bytes;
     LS_CUDA_TRY(cudaFuncSetAttribute(k_test_fft<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k_test_fft<N><<<(unsigned)(nlines / GeoA<N>::LPC), GeoA<N>::THREADS, smem>>>(d_in, d_out, d_W, roundtrip);
     LS_CUDA_TRY(cudaGetLastError());
@@ -48,7 +52,7 @@ extern "C" int ls_test_fft_lines(int64_t N, int64_t nlines, const ls_cdouble* in
     LS_REQUIRE(nlines > 0 && nlines % 16 == 0, LS_ERR_INVALID, "ls_test_fft_lines: nlines must be a positive multiple of 16");
     const size_t bytes = (size_t)N * nlines * sizeof(cd);
     cd *d_in = nullptr, *d_out = nullptr, *d_W = nullptr;
-    auto W = twiddle_table(N, N);
+    auto W = engine_table((int)N);
     LS_CUDA_TRY(cudaMalloc(&d_in, bytes));
     LS_CUDA_TRY(cudaMalloc(&d_out, bytes));
     LS_CUDA_TRY(cudaMalloc(&d_W, W.size() * sizeof(cd)));
