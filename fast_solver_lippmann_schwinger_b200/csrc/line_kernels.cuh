@@ -71,6 +71,7 @@ template <int N, bool MODE_B> struct Smem {
     static constexpr int TW1N = EngTab<N>::TW1N;
     static constexpr int fwd_bytes = (LPC * N + TW1N) * (int)sizeof(cd);
     static constexpr int mid_bytes = (3 * LPC * N + TW1N) * (int)sizeof(cd) + 16;
+    static constexpr int mid_bytes_direct = (2 * LPC * N + TW1N) * (int)sizeof(cd) + 16;
 };
 
 // ---- forward, pruned: N inputs -> 4N slots -------------------------------------------
@@ -124,8 +125,8 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
 //       -> per (unit, r) one contiguous chunk, fetched by TMA bulk copy into shared memory
 //          while the previous block's inverse transform runs.
 // out : line L point j at out[L*out_ls + j*out_es]  (may alias in when strides agree)
-template <int N, bool MODE_B>
-__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
+template <int N, bool MODE_B, bool GSM = true, int MINB = 1>
+__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MINB)
 k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB,
             long in_ls, long in_es, long out_ls, long out_es, long line0) {
     typedef Map<N, MODE_B> M;
@@ -136,8 +137,8 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     M mp;
     cd* ex = sm + sm_group_off(mp);
     cd* xs = sm + LPC * N + sm_group_off(mp);   // thread-private copy of the input line
-    cd* gb = sm + 2 * LPC * N;                  // spectrum chunk(s) of the current r
-    cd* tw1 = sm + 3 * LPC * N;
+    cd* gb = sm + 2 * LPC * N;                  // spectrum chunk(s) of the current r (GSM only)
+    cd* tw1 = sm + (GSM ? 3 : 2) * LPC * N;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(tw1 + Smem<N, MODE_B>::TW1N);
     const long Lcta = line0 + (long)blockIdx.x * LPC;
     const long L = Lcta + mp.line;
@@ -150,7 +151,7 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
         for (int u = 0; u < UPC; ++u)
             bulk_g2s(gb + u * UNIT, gsrc + ((long)u * 4 + r) * UNIT, (unsigned)(UNIT * sizeof(cd)), bar);
     };
-    if (threadIdx.x == 0) {
+    if (GSM && threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_proxy_async();
         issue_g(0);
@@ -171,6 +172,13 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
 #pragma unroll
         for (int a = 0; a < E; ++a) v[a] = xs[mp.lay.phys(a * T + t)];
         fft_fwd<N>(v, t, r, ex, mp.lay, tw);
+        if (!GSM) {
+            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * 4 + r) * UNIT + mp.lay_lam()
+                                 : gsrc + ((long)mp.line * 4 + r) * UNIT;
+            constexpr int gs = MODE_B ? 8 : 1;
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], __ldg(&g[(t + T * e) * gs]));
+        } else {
         mbar_wait(bar, (unsigned)(r & 1));
         if (MODE_B) {
             const cd* g = gb + sm_group_off(mp);
@@ -181,9 +189,10 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
 #pragma unroll
             for (int e = 0; e < E; ++e) v[e] = cmul(v[e], g[t + T * e]);
         }
+        }
         fft_inv<N>(v, t, r, ex, mp.lay, tw, [&]() {
             // every thread has consumed gb (the multiply precedes this barrier): refill it
-            if (r < 3 && threadIdx.x == 0) {
+            if (GSM && r < 3 && threadIdx.x == 0) {
                 fence_proxy_async();
                 issue_g(r + 1);
             }

@@ -58,21 +58,29 @@ template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
     op->launches++;
     return LS_OK;
 }
-template <int N> int launch_mid(Op2D* op) {
-    constexpr int smem = Smem<N, false>::mid_bytes;
+template <int N, bool GSM, int MINB> int launch_mid_v(Op2D* op) {
+    constexpr int smem = GSM ? Smem<N, false>::mid_bytes : Smem<N, false>::mid_bytes_direct;
     static bool attr = false;
     if (!attr) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false, GSM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     dim3 grid((unsigned)(op->ne / GeoA<N>::LPC));
     // line = x slot sx; point j at A[sx + ne*j]; output line contiguous C[j + m*sx]
     op->phase_begin(1);
-    k_mid_fused<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
+    k_mid_fused<N, false, GSM, MINB><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
         op->d_A, op->d_C, op->d_G, op->d_TABm, 1, op->ne, op->m, 1, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
+}
+template <int N> int launch_mid(Op2D* op) {
+    static int variant = -1;
+    // variants measured on B200 at 2048^2 (profiles/r1_b_notes.md): 1 = spectrum straight from HBM into
+    // registers (0.706 ms), 0 = spectrum staged in shared memory by TMA bulk copies (0.761 ms)
+    if (variant < 0) { const char* e = getenv("LS_P2_VARIANT"); variant = e ? atoi(e) : 1; }
+    if (variant == 0) return launch_mid_v<N, true, 1>(op);
+    return launch_mid_v<N, false, 1>(op);
 }
 template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
     constexpr int smem = Smem<N, false>::fwd_bytes;
