@@ -24,6 +24,19 @@ APPLY_FASTCONVOLUTION, APPLY_FFTCONVOLUTION = 0, 1
 QUADRULES = {"trapezoidal": QUAD_TRAPEZOIDAL, "Greengard_Vico": QUAD_GREENGARD_VICO}
 
 
+class CDouble(C.Structure):
+    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+
+    @classmethod
+    def of(cls, z):
+        z = complex(z)
+        return cls(z.real, z.imag)
+
+
+# typedef int (*ls_solve_cb)(void* user, ls_cdouble* v_inout, int64_t n)
+SOLVE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+
+
 class LSCudaError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libls_cuda error %d: %s" % (code, msg))
@@ -70,6 +83,17 @@ def lib():
         "ls_op2d_create": (ci, [C.POINTER(vp), i64, i64, i64, i64, vp, vp, dbl, ci, ci]),
         "ls_op2d_apply": (ci, [vp, vp, vp, ci, ci]),
         "ls_op_size": (ci, [vp, C.POINTER(i64)]),
+        "ls_spm_create": (ci, [C.POINTER(vp), i64, i64, vp, vp, vp]),
+        "ls_spm_mv": (ci, [vp, CDouble, vp, CDouble, vp, ci]),
+        "ls_spm_info": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "ls_krylov_create": (ci, [C.POINTER(vp), i64]),
+        "ls_zdotc": (ci, [vp, vp, vp, C.POINTER(CDouble)]),
+        "ls_dznrm2": (ci, [vp, vp, C.POINTER(dbl)]),
+        "ls_zaxpy": (ci, [vp, CDouble, vp, vp]),
+        "ls_zscal": (ci, [vp, CDouble, vp]),
+        "ls_mgs_step": (ci, [vp, vp, i64, ci, vp, vp]),
+        "ls_gmres": (ci, [vp, vp, vp, SOLVE_CB, vp, vp, vp, ci, i64, dbl, dbl, ci, vp, i64,
+                          C.POINTER(i64), C.POINTER(ci), C.POINTER(i64), ci]),
         "ls_destroy": (ci, [vp]),
         "ls_sync": (ci, [vp]),
         "ls_timer_start": (ci, [vp]),

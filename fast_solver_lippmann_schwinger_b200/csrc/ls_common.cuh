@@ -47,6 +47,12 @@ struct HandleBase {
     std::vector<void*> host_allocs;   // pinned staging
 
     virtual int64_t op_size() const { return -1; }
+    // operator handles: y = M*b (mode 0) / FFTconvolution (mode 1) on device pointers, on `stream`
+    virtual int apply_dev(const cd* b, cd* y, int mode) {
+        (void)b; (void)y; (void)mode;
+        set_error("handle is not an operator");
+        return LS_ERR_INVALID;
+    }
 
     // optional per-phase CUDA-event profiling (bench roofline of the dominant kernel)
     bool profiling = false;

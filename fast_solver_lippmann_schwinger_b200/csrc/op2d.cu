@@ -24,6 +24,7 @@ struct Op2D : HandleBase {
     cd* d_C = nullptr;        // m x ne (line contiguous)
     cd* d_b = nullptr; cd* d_y = nullptr;   // staging for host-pointer applies
     int64_t op_size() const override { return n * m; }
+    int apply_dev(const cd* b, cd* y, int mode) override;
 };
 
 // Gd[(sx*4 + ry)*m + sy] = GFFT[(4 fx[sx%n] + sx/n + ne/2) % ne, (4 fy[sy] + ry + me/2) % me] / (ne*me)
@@ -130,6 +131,8 @@ int apply_device(Op2D* op, const cd* b, cd* y, int mode) {
 }
 
 }  // namespace
+
+int Op2D::apply_dev(const cd* b, cd* y, int mode) { return apply_device(this, b, y, mode); }
 
 extern "C" {
 

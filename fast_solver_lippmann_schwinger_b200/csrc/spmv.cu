@@ -1,0 +1,148 @@
+// Sparsifying-matrix SpMV  y <- alpha*A*x + beta*y   (complex128, banded 9-/27-point stencil matrix).
+// Stands behind `M.As*b` at preconditioner.jl:138,142,159,163 and mirrors the signature of
+// SparseBLAS.cscmv!('N', alpha, "GXXF", A, x, beta, y) (sparseblas.jl:14-25).
+//
+// The matrix arrives exactly as Julia holds it (SparseMatrixCSC{ComplexF64,Int64}: 1-based colptr,
+// rowval, nzval) and is converted once to CSR with 32-bit column indices.  Kernel: a sub-warp of
+// LPR lanes per row (8 lanes for the 9-point 2-D matrix, 32 for the 27-point 3-D one), 128-bit
+// coalesced value loads, warp-shuffle reduction in a fixed order (deterministic).
+// Algorithmic bytes: nnz*20 + 4(N+1) + 32N  (SURVEY.md section 8(d)).
+#include "ls_common.cuh"
+#include "spmv.cuh"
+#include <algorithm>
+
+using namespace ls;
+
+namespace ls {
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_spmv_csr(const int* __restrict__ rowptr, const int* __restrict__ col, const cd* __restrict__ val,
+           const cd* __restrict__ x, cd* y, cd alpha, cd beta, int use_beta, long nrows) {
+    const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long row = gt / LPR;
+    const int lane = (int)(gt % LPR);
+    double sr = 0.0, si = 0.0;
+    if (row < nrows) {
+        const int p0 = rowptr[row], p1 = rowptr[row + 1];
+        for (int p = p0 + lane; p < p1; p += LPR) {
+            const cd a = __ldg(&val[p]);
+            const cd xv = __ldg(&x[__ldg(&col[p])]);
+            sr += a.x * xv.x - a.y * xv.y;
+            si += a.x * xv.y + a.y * xv.x;
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o, LPR);
+        si += __shfl_xor_sync(0xffffffffu, si, o, LPR);
+    }
+    if (row < nrows && lane == 0) {
+        cd r = make_double2(alpha.x * sr - alpha.y * si, alpha.x * si + alpha.y * sr);
+        if (use_beta) {
+            const cd y0 = y[row];
+            r.x += beta.x * y0.x - beta.y * y0.y;
+            r.y += beta.x * y0.y + beta.y * y0.x;
+        }
+        y[row] = r;
+    }
+}
+
+int SpM::mv_dev(cd alpha, const cd* x, cd beta, cd* y, cudaStream_t s) {
+    const int use_beta = (beta.x != 0.0 || beta.y != 0.0) ? 1 : 0;
+    const int th = 256;
+    if (lanes_per_row == 8) {
+        long blocks = (nrows * 8 + th - 1) / th;
+        k_spmv_csr<8><<<(unsigned)blocks, th, 0, s>>>(d_rowptr, d_col, d_val, x, y, alpha, beta, use_beta, nrows);
+    } else {
+        long blocks = (nrows * 32 + th - 1) / th;
+        k_spmv_csr<32><<<(unsigned)blocks, th, 0, s>>>(d_rowptr, d_col, d_val, x, y, alpha, beta, use_beta, nrows);
+    }
+    launches++;
+    LS_CUDA_TRY(cudaGetLastError());
+    return LS_OK;
+}
+
+}  // namespace ls
+
+extern "C" {
+
+int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* colptr, const int64_t* rowval,
+                  const ls_cdouble* nzval) {
+    LS_REQUIRE(out && colptr && rowval && nzval, LS_ERR_INVALID, "ls_spm_create: null pointer");
+    LS_REQUIRE(nrows > 0 && ncols > 0, LS_ERR_INVALID, "ls_spm_create: non-positive size");
+    LS_REQUIRE(colptr[0] == 1, LS_ERR_INVALID, "ls_spm_create: colptr must be 1-based (Julia SparseMatrixCSC)");
+    const int64_t nnz = colptr[ncols] - 1;
+    LS_REQUIRE(nnz >= 0 && nnz < (int64_t)2147483647 && ncols < (int64_t)2147483647, LS_ERR_UNSUPPORTED,
+               "ls_spm_create: nnz=%ld exceeds the 32-bit index range of the device format", (long)nnz);
+    // CSC (1-based) -> CSR (0-based, int32), columns ascending inside each row: the same summation
+    // order per output row as SparseArrays' column-scatter loop
+    std::vector<int> rowptr((size_t)nrows + 1, 0);
+    for (int64_t c = 0; c < ncols; ++c) {
+        LS_REQUIRE(colptr[c + 1] >= colptr[c], LS_ERR_INVALID, "ls_spm_create: colptr not monotone at column %ld", (long)c);
+        for (int64_t p = colptr[c] - 1; p < colptr[c + 1] - 1; ++p) {
+            const int64_t r = rowval[p] - 1;
+            LS_REQUIRE(r >= 0 && r < nrows, LS_ERR_INVALID, "ls_spm_create: row index %ld out of range", (long)(r + 1));
+            rowptr[(size_t)r + 1]++;
+        }
+    }
+    for (int64_t r = 0; r < nrows; ++r) rowptr[(size_t)r + 1] += rowptr[(size_t)r];
+    std::vector<int> col((size_t)nnz), next(rowptr.begin(), rowptr.end() - 1);
+    std::vector<cd> val((size_t)nnz);
+    const cd* nz = reinterpret_cast<const cd*>(nzval);
+    for (int64_t c = 0; c < ncols; ++c)
+        for (int64_t p = colptr[c] - 1; p < colptr[c + 1] - 1; ++p) {
+            const int64_t r = rowval[p] - 1;
+            const int q = next[(size_t)r]++;
+            col[(size_t)q] = (int)c;
+            val[(size_t)q] = nz[p];
+        }
+    SpM* A = new SpM();
+    int rc = A->init_base(KIND_SPM);
+    if (rc) { delete A; return rc; }
+    A->nrows = nrows; A->ncols = ncols; A->nnz = nnz;
+    const double avg = (double)nnz / (double)nrows;
+    A->lanes_per_row = avg <= 12.0 ? 8 : 32;
+#define TRY(x) do { rc = (x); if (rc) { delete A; return rc; } } while (0)
+    TRY(A->dupload((void**)&A->d_rowptr, rowptr.data(), rowptr.size() * sizeof(int)));
+    TRY(A->dupload((void**)&A->d_col, col.data(), std::max<size_t>(col.size(), 1) * sizeof(int)));
+    TRY(A->dupload((void**)&A->d_val, val.data(), std::max<size_t>(val.size(), 1) * sizeof(cd)));
+    TRY(A->dmalloc((void**)&A->d_x, (size_t)ncols * sizeof(cd)));
+    TRY(A->dmalloc((void**)&A->d_y, (size_t)nrows * sizeof(cd)));
+#undef TRY
+    *out = reinterpret_cast<ls_handle>(A);
+    return LS_OK;
+}
+
+int ls_spm_mv(ls_handle h, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble beta, ls_cdouble* y, int memloc) {
+    LS_REQUIRE(h && x && y, LS_ERR_INVALID, "ls_spm_mv: null argument");
+    SpM* A = reinterpret_cast<SpM*>(h);
+    LS_REQUIRE(A->kind == KIND_SPM, LS_ERR_INVALID, "ls_spm_mv: not a sparse-matrix handle");
+    LS_CUDA_TRY(cudaSetDevice(A->device));
+    const cd al = make_double2(alpha.re, alpha.im), be = make_double2(beta.re, beta.im);
+    if (memloc == LS_MEM_DEVICE) {
+        LS_REQUIRE((const void*)x != (const void*)y, LS_ERR_INVALID, "ls_spm_mv: x and y must not alias");
+        return A->mv_dev(al, reinterpret_cast<const cd*>(x), be, reinterpret_cast<cd*>(y), A->stream);
+    }
+    LS_REQUIRE(memloc == LS_MEM_HOST, LS_ERR_INVALID, "ls_spm_mv: unknown memloc %d", memloc);
+    LS_CUDA_TRY(cudaMemcpyAsync(A->d_x, x, (size_t)A->ncols * sizeof(cd), cudaMemcpyHostToDevice, A->stream));
+    if (be.x != 0.0 || be.y != 0.0)
+        LS_CUDA_TRY(cudaMemcpyAsync(A->d_y, y, (size_t)A->nrows * sizeof(cd), cudaMemcpyHostToDevice, A->stream));
+    int rc = A->mv_dev(al, A->d_x, be, A->d_y, A->stream);
+    if (rc) return rc;
+    LS_CUDA_TRY(cudaMemcpyAsync(y, A->d_y, (size_t)A->nrows * sizeof(cd), cudaMemcpyDeviceToHost, A->stream));
+    LS_CUDA_TRY(cudaStreamSynchronize(A->stream));
+    return LS_OK;
+}
+
+int ls_spm_info(ls_handle h, int64_t* nrows, int64_t* ncols, int64_t* nnz) {
+    LS_REQUIRE(h, LS_ERR_INVALID, "ls_spm_info: null handle");
+    SpM* A = reinterpret_cast<SpM*>(h);
+    LS_REQUIRE(A->kind == KIND_SPM, LS_ERR_INVALID, "ls_spm_info: not a sparse-matrix handle");
+    if (nrows) *nrows = A->nrows;
+    if (ncols) *ncols = A->ncols;
+    if (nnz) *nnz = A->nnz;
+    return LS_OK;
+}
+
+}  // extern "C"

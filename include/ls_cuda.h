@@ -77,6 +77,46 @@ int ls_op2d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int
 /* size(M,dim) / eltype, FastConvolution.jl:31-41: writes N = n*m */
 int ls_op_size(ls_handle h, int64_t* N);
 
+/* ---- sparsifying matrix As: SparseMatrixCSC{ComplexF64,Int64}, preconditioner.jl:27-30 ------ *
+ * Arrays exactly as Julia holds them (A.colptr, A.rowval, A.nzval; 1-based).  Converted once
+ * to CSR/int32 on the device.                                                              */
+int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* colptr,
+                  const int64_t* rowval, const ls_cdouble* nzval);
+/* y <- alpha*A*x + beta*y : `M.As*b` (preconditioner.jl:138,142,159,163) is alpha=1, beta=0;
+ * same meaning as SparseBLAS.cscmv!('N', alpha, "GXXF", A, x, beta, y), sparseblas.jl:14-25.
+ * x and y must not alias.                                                                  */
+int ls_spm_mv(ls_handle A, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble beta, ls_cdouble* y, int memloc);
+int ls_spm_info(ls_handle A, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+
+/* ---- GMRES Arnoldi vector kernels (IterativeSolvers.jl gmres!, un-vendored; call sites ------ *
+ * examples/example.jl:85,91).  A Krylov workspace owns the reduction buffers for vectors of
+ * length n.  All vector pointers below are DEVICE pointers (ls_dev_alloc).                  */
+int ls_krylov_create(ls_handle* out, int64_t n);
+int ls_zdotc(ls_handle k, const ls_cdouble* x, const ls_cdouble* y, ls_cdouble* result);   /* sum conj(x) y */
+int ls_dznrm2(ls_handle k, const ls_cdouble* x, double* result);
+int ls_zaxpy(ls_handle k, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble* y);           /* y += alpha x */
+int ls_zscal(ls_handle k, ls_cdouble alpha, ls_cdouble* x);
+/* orthogonalize_and_normalize!(V[:,1:k], w, h) with ModifiedGramSchmidt: for i<k: h[i] = dot(V_i,w),
+ * w -= h[i] V_i; h[k] = norm(w); w /= h[k].  V is column-major with leading dimension ldv.
+ * hcol receives k+1 complex values (the last one real).                                     */
+int ls_mgs_step(ls_handle k, const ls_cdouble* V, int64_t ldv, int kcols, ls_cdouble* w, ls_cdouble* hcol);
+
+/* Host callback applying Msp^-1 in place on a HOST vector of n complex values (the sparse direct
+ * solve `MspInv \ .` of preconditioner.jl:138,159 stays with the caller: UMFPACK / PARDISO /
+ * SuperLU).  Return 0 on success.                                                           */
+typedef int (*ls_solve_cb)(void* user, ls_cdouble* v_inout, int64_t n);
+
+/* gmres!(x, A, b; Pl, abstol, reltol, restart, maxiter, log=true, initially_zero) with the Krylov
+ * basis resident on the GPU.  A = operator handle; left preconditioner ldiv!(Pl, v) =
+ * msp_solve(As*v) (preconditioner.jl:147-166): `As` nullable, `msp_solve` nullable.
+ * restart <= 0 -> min(20, N); maxiter <= 0 -> N (inner iterations); reltol as given
+ * (upstream default sqrt(eps)).  resnorm_hist receives the logged residual per inner
+ * iteration (history[:resnorm], example.jl:86).  b, x: host or device per memloc.           */
+int ls_gmres(ls_handle krylov, ls_handle op, ls_handle As, ls_solve_cb msp_solve, void* user,
+             const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol,
+             double abstol, int initially_zero, double* resnorm_hist, int64_t hist_cap,
+             int64_t* niter, int* converged, int64_t* mv_products, int memloc);
+
 /* ---- handle services ------------------------------------------------------------------ */
 int ls_destroy(ls_handle h);
 int ls_sync(ls_handle h);
