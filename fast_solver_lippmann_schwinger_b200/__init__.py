@@ -4,6 +4,6 @@ Only what the path needs lives here: ``csrc/`` (CUDA kernels + the C ABI of incl
 ``_lib`` (ctypes binding) and ``operators`` / ``krylov`` (the reference's operator interface).
 """
 from ._lib import (DeviceBuffer, LSCudaError, LSUnsupported, PinnedArray, declared_symbols, lib)  # noqa: F401
-from .operators import FastM, FFTconvolution, fastconvolution, mul_  # noqa: F401
+from .operators import FastM, FastM3D, FFTconvolution, fastconvolution, mul_  # noqa: F401
 from .krylov import (ConvergenceHistory, GPUSparseMatrixCSC, KrylovWorkspace, SparsifyingPreconditioner,  # noqa: F401
                      cscmv_, gmres_)

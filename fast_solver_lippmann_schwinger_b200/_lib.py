@@ -82,6 +82,8 @@ def lib():
         "ls_host_free_pinned": (ci, [vp]),
         "ls_op2d_create": (ci, [C.POINTER(vp), i64, i64, i64, i64, vp, vp, dbl, ci, ci]),
         "ls_op2d_apply": (ci, [vp, vp, vp, ci, ci]),
+        "ls_op3d_create": (ci, [C.POINTER(vp), i64, i64, i64, i64, i64, i64, vp, vp, dbl, dbl, dbl, ci]),
+        "ls_op3d_apply": (ci, [vp, vp, vp, ci, ci]),
         "ls_op_size": (ci, [vp, C.POINTER(i64)]),
         "ls_spm_create": (ci, [C.POINTER(vp), i64, i64, vp, vp, vp]),
         "ls_spm_mv": (ci, [vp, CDouble, vp, CDouble, vp, ci]),

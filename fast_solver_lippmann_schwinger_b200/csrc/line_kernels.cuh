@@ -65,6 +65,16 @@ template <int N> struct Map<N, true> {
 template <int N> __device__ __forceinline__ int sm_group_off(const Map<N, false>&) { return 0; }
 template <int N> __device__ __forceinline__ int sm_group_off(const Map<N, true>& m) { return m.smoff; }
 
+// Two-level line addressing: line L = l0 + ldim0*l1 starts at l0*ls0 + l1*ls1; its points/slots
+// are `es` elements apart.  (2-D uses one level; 3-D y-lines are indexed by (x slot, z plane).)
+struct LineAddr {
+    long ldim0;
+    long in_ls0, in_ls1, in_es;
+    long out_ls0, out_ls1, out_es;
+};
+__device__ __forceinline__ long line_in(const LineAddr& a, long L) { return (L % a.ldim0) * a.in_ls0 + (L / a.ldim0) * a.in_ls1; }
+__device__ __forceinline__ long line_out(const LineAddr& a, long L) { return (L % a.ldim0) * a.out_ls0 + (L / a.ldim0) * a.out_ls1; }
+
 // per-CTA shared memory: [exchange: LPC*N][(mid only) x copy: LPC*N][(mid only) spectrum: LPC*N][tw1][mbarrier]
 template <int N, bool MODE_B> struct Smem {
     static constexpr int LPC = MODE_B ? GeoB<N>::LPC : GeoA<N>::LPC;
@@ -80,8 +90,7 @@ template <int N, bool MODE_B> struct Smem {
 template <int N, bool MODE_B>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
 k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __restrict__ out,
-             const cd* __restrict__ TAB,
-             long in_ls, long in_es, long out_ls, long out_es, long line0) {
+             const cd* __restrict__ TAB, const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
     constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
     extern __shared__ __align__(128) cd sm[];
@@ -92,10 +101,12 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
     const long L = line0 + (long)blockIdx.x * LPC + mp.line;
     const int t = mp.t;
     const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    const long in_base = line_in(la, L), out_base = line_out(la, L);
+    const long in_es = la.in_es, out_es = la.out_es;
     cd x[E];
 #pragma unroll
     for (int a = 0; a < E; ++a) {
-        long off = L * in_ls + (long)(a * T + t) * in_es;
+        long off = in_base + (long)(a * T + t) * in_es;
         cd val = in[off];
         if (nu != nullptr) {
             double s = nu[off];
@@ -111,7 +122,7 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
 #pragma unroll
         for (int a = 0; a < E; ++a) v[a] = x[a];
         fft_fwd<N>(v, t, r, ex, mp.lay, tw);
-        cd* o = out + L * out_ls + (long)(r * N + t) * out_es;
+        cd* o = out + out_base + (long)(r * N + t) * out_es;
 #pragma unroll
         for (int e = 0; e < E; ++e) o[(long)(T * e) * out_es] = v[e];
         __syncthreads();   // next forward rewrites the exchange buffer at other addresses
@@ -128,7 +139,7 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
 template <int N, bool MODE_B, bool GSM = true, int MINB = 1>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MINB)
 k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB,
-            long in_ls, long in_es, long out_ls, long out_es, long line0) {
+            const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
     constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
     constexpr int UNIT = MODE_B ? 8 * N : N;          // points per spectrum chunk
@@ -159,9 +170,9 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     load_tw1<N>(tw1, TAB);
     const TwState<N> tw = make_tw<N>(t, TAB, tw1);
     {
-        const cd* p = in + L * in_ls + (long)t * in_es;
+        const cd* p = in + line_in(la, L) + (long)t * la.in_es;
 #pragma unroll
-        for (int a = 0; a < E; ++a) xs[mp.lay.phys(a * T + t)] = p[(long)(a * T) * in_es];
+        for (int a = 0; a < E; ++a) xs[mp.lay.phys(a * T + t)] = p[(long)(a * T) * la.in_es];
     }
     __syncthreads();   // tw1 + mbarrier init visible
     cd acc[E];
@@ -199,9 +210,9 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
         });
         demod_accumulate<N>(acc, v, r);
     }
-    cd* o = out + L * out_ls + (long)t * out_es;
+    cd* o = out + line_out(la, L) + (long)t * la.out_es;
 #pragma unroll
-    for (int a = 0; a < E; ++a) o[(long)(a * T) * out_es] = acc[a];
+    for (int a = 0; a < E; ++a) o[(long)(a * T) * la.out_es] = acc[a];
 }
 
 // ---- inverse, pruned: 4N slots -> N outputs, optional identity-plus-contrast combine --
@@ -210,7 +221,7 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
 template <int N, bool MODE_B>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
 k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __restrict__ TAB, double scale,
-             long in_ls, long in_es, long out_ls, long out_es, long line0) {
+             const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
     constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
     extern __shared__ __align__(128) cd sm[];
@@ -222,24 +233,75 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __res
     const int t = mp.t;
     const TwState<N> tw = make_tw<N>(t, TAB, tw1);
     __syncthreads();
+    const long in_base = line_in(la, L), out_base = line_out(la, L);
     cd acc[E];
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
         cd v[E];
-        const cd* p = in + L * in_ls + (long)(r * N + t) * in_es;
+        const cd* p = in + in_base + (long)(r * N + t) * la.in_es;
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = p[(long)(T * e) * in_es];
+        for (int e = 0; e < E; ++e) v[e] = p[(long)(T * e) * la.in_es];
         fft_inv<N>(v, t, r, ex, mp.lay, tw);
         demod_accumulate<N>(acc, v, r);
         __syncthreads();
     }
 #pragma unroll
     for (int a = 0; a < E; ++a) {
-        long off = L * out_ls + (long)(a * T + t) * out_es;
+        long off = out_base + (long)(a * T + t) * la.out_es;
         cd res = cscale(acc[a], scale);
         if (bsrc != nullptr) res = cadd(res, bsrc[off]);
         out[off] = res;
     }
+}
+
+}  // namespace lsk
+
+// ---- host-side launchers ----------------------------------------------------------------
+namespace lsk {
+
+template <int N, bool B>
+inline cudaError_t launch_fwd(cudaStream_t s, long nlines, const cd* in, const double* nu, cd* out, const cd* TAB,
+                              const LineAddr& la) {
+    constexpr int smem = Smem<N, B>::fwd_bytes;
+    constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_fwd_pruned<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    k_fwd_pruned<N, B><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, nu, out, TAB, la, 0);
+    return cudaPeekAtLastError();
+}
+
+template <int N, bool B, bool GSM>
+inline cudaError_t launch_mid(cudaStream_t s, long nlines, const cd* in, cd* out, const cd* G, const cd* TAB,
+                              const LineAddr& la) {
+    constexpr int smem = GSM ? Smem<N, B>::mid_bytes : Smem<N, B>::mid_bytes_direct;
+    constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_mid_fused<N, B, GSM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    k_mid_fused<N, B, GSM, 1><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, out, G, TAB, la, 0);
+    return cudaPeekAtLastError();
+}
+
+template <int N, bool B>
+inline cudaError_t launch_inv(cudaStream_t s, long nlines, const cd* in, const cd* bsrc, cd* out, const cd* TAB,
+                              double scale, const LineAddr& la) {
+    constexpr int smem = Smem<N, B>::fwd_bytes;
+    constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_inv_pruned<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    k_inv_pruned<N, B><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, bsrc, out, TAB, scale, la, 0);
+    return cudaPeekAtLastError();
 }
 
 }  // namespace lsk

@@ -54,7 +54,7 @@ template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
     op->phase_begin(0);
     k_fwd_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        b, nu, op->d_A, op->d_TABn, op->n, 1, op->ne, 1, 0);
+        b, nu, op->d_A, op->d_TABn, LineAddr{1L << 40, op->n, 0, 1, op->ne, 0, 1}, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
@@ -70,7 +70,7 @@ template <int N, bool GSM, int MINB> int launch_mid_v(Op2D* op) {
     // line = x slot sx; point j at A[sx + ne*j]; output line contiguous C[j + m*sx]
     op->phase_begin(1);
     k_mid_fused<N, false, GSM, MINB><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        op->d_A, op->d_C, op->d_G, op->d_TABm, 1, op->ne, op->m, 1, 0);
+        op->d_A, op->d_C, op->d_G, op->d_TABm, LineAddr{1L << 40, 1, 0, op->ne, op->m, 0, 1}, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
@@ -94,7 +94,7 @@ template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
     // line = column j; slot sx at C[j + m*sx]
     op->phase_begin(2);
     k_inv_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        op->d_C, bsrc, y, op->d_TABn, scale, 1, op->m, op->n, 1, 0);
+        op->d_C, bsrc, y, op->d_TABn, scale, LineAddr{1L << 40, 1, 0, op->m, op->n, 0, 1}, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;

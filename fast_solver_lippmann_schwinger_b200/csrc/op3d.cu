@@ -1,0 +1,237 @@
+// 3-D Lippmann-Schwinger operator  y = b + omega^2 * G (nu .* b)  on one B200 (slab-ready layout).
+// Stands behind struct FastM3D, its `*` and FFTconvolution (reference FastConvolution3D.jl:7-63).
+// Five launches per apply (pruned 4x zero padding in every dimension, see line_kernels.cuh):
+//   P1 k_fwd_pruned<n,A>  x lines (contiguous)   b,nu [n m l]      -> A1 [ne m l]
+//   P2 k_fwd_pruned<m,B>  y lines (8 x-slots/warp quarter)  A1     -> A2 [ne me l]
+//   P3 k_mid_fused <l,B>  z lines, fused spectrum multiply, in place on A2 (reads G [ne me le])
+//   P4 k_inv_pruned<m,B>  y lines                 A2               -> C1 [ne m l]   (reuses A1)
+//   P5 k_inv_pruned<n,A>  x lines + combine       C1, b            -> y
+// Algorithmic HBM bytes per apply: 2360*N; the spectrum read is 1024*N of it.
+#include "ls_common.cuh"
+#include "line_kernels.cuh"
+
+using namespace ls;
+using namespace lsk;
+
+namespace {
+
+struct Op3D : HandleBase {
+    long n = 0, m = 0, l = 0, ne = 0, me = 0, le = 0;
+    double omega = 0;
+    double* d_nu = nullptr;
+    cd* d_G = nullptr;                 // [unit = (sx + ne*sy)/8][rz][slot_z][8]  scaled by 1/(ne me le)
+    cd *d_TABn = nullptr, *d_TABm = nullptr, *d_TABl = nullptr;
+    cd* d_A1 = nullptr;                // ne x m x l   (also C1)
+    cd* d_A2 = nullptr;                // ne x me x l
+    cd* d_b = nullptr; cd* d_y = nullptr; cd* d_tmp = nullptr;
+    int64_t op_size() const override { return n * m * l; }
+    int apply_dev(const cd* b, cd* y, int mode) override;
+};
+
+struct GenParams {
+    long n, m, l, ne, me, le;
+    double dk;          // 2 pi / Lp
+    double L, k;        // truncation radius, wave number
+    double eLk_re, eLk_im;
+    double scale;
+};
+
+// Gtruncated3D (Functions.jl:49-51) at |(kx,ky,kz)|, numpy-sinc argument path of the oracle
+__device__ __forceinline__ cd gtrunc3d(double s, const GenParams& p) {
+    const double PI = 3.141592653589793;
+    const double Ls = p.L * s;
+    const double c = cos(Ls);
+    double sinc;
+    {
+        const double xs = Ls / PI;
+        const double yv = PI * xs;
+        sinc = (xs == 0.0) ? 1.0 : sin(yv) / yv;
+    }
+    // -1 + e^{iLk} (c - i k L sinc)
+    const double ar = c, ai = -(p.k * p.L * sinc);
+    const double nr = -1.0 + (p.eLk_re * ar - p.eLk_im * ai);
+    const double ni = p.eLk_re * ai + p.eLk_im * ar;
+    const double den = p.k * p.k - s * s;
+    return make_double2(nr / den, ni / den);
+}
+
+// fills the device spectrum in its final layout, either by gathering from the reference-ordered
+// array `gin` (ne x me x le, centred) or by evaluating the Greengard-Vico formula.
+__global__ void k_fill_g3d(const cd* __restrict__ gin, cd* __restrict__ gout, const int* __restrict__ fx,
+                           const int* __restrict__ fy, const int* __restrict__ fz, GenParams p) {
+    const long total = p.ne * p.me * p.le;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long lam = idx & 7;
+        long q = idx >> 3;
+        const long sz = q % p.l; q /= p.l;
+        const long rz = q & 3;
+        const long unit = q >> 2;
+        const long Lidx = unit * 8 + lam;
+        const long sx = Lidx % p.ne, sy = Lidx / p.ne;
+        const long kx = 4L * fx[sx % p.n] + sx / p.n;
+        const long ky = 4L * fy[sy % p.m] + sy / p.m;
+        const long kz = 4L * fz[sz] + rz;
+        const long ix = (kx + p.ne / 2) % p.ne, iy = (ky + p.me / 2) % p.me, iz = (kz + p.le / 2) % p.le;
+        cd v;
+        if (gin != nullptr) {
+            v = gin[ix + p.ne * (iy + p.me * iz)];
+        } else {
+            const double kxv = p.dk * (double)(ix - p.ne / 2);
+            const double kyv = p.dk * (double)(iy - p.me / 2);
+            const double kzv = p.dk * (double)(iz - p.le / 2);
+            const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv)), __dmul_rn(kzv, kzv));
+            v = gtrunc3d(sqrt(s2), p);
+        }
+        gout[idx] = make_double2(v.x * p.scale, v.y * p.scale);
+    }
+}
+
+#define LS3_DISPATCH(N_, CALL)                                          \
+    switch (N_) {                                                       \
+        case 64:  e = CALL(64); break;                                  \
+        case 128: e = CALL(128); break;                                 \
+        case 256: e = CALL(256); break;                                 \
+        case 512: e = CALL(512); break;                                 \
+        default: set_error("unsupported 3-D size %ld", (long)(N_)); return LS_ERR_UNSUPPORTED; \
+    }
+
+int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
+    cudaError_t e = cudaSuccess;
+    cudaStream_t s = op->stream;
+    const long n = op->n, m = op->m, l = op->l, ne = op->ne, me = op->me;
+    const bool full = (mode == LS_APPLY_FASTCONVOLUTION);
+    // P1: x lines (j,p): in b[n*(j + m p) + i]; out A1[ne*(j + m p) + sx]
+    {
+        LineAddr la{1L << 40, n, 0, 1, ne, 0, 1};
+        op->phase_begin(0);
+#define C1(N) launch_fwd<N, false>(s, m * l, b, full ? op->d_nu : nullptr, op->d_A1, op->d_TABn, la)
+        LS3_DISPATCH(n, C1);
+        op->phase_end(); op->launches++;
+        LS_CUDA_TRY(e);
+    }
+    // P2: y lines (sx,p): in A1[sx + ne*m*p + ne*j]; out A2[sx + ne*me*p + ne*sy]
+    {
+        LineAddr la{ne, 1, ne * m, ne, 1, ne * me, ne};
+        op->phase_begin(1);
+#define C2(N) launch_fwd<N, true>(s, ne * l, op->d_A1, nullptr, op->d_A2, op->d_TABm, la)
+        LS3_DISPATCH(m, C2);
+        op->phase_end(); op->launches++;
+        LS_CUDA_TRY(e);
+    }
+    // P3: z lines L = sx + ne*sy: point p at A2[L + ne*me*p], in place
+    {
+        LineAddr la{1L << 40, 1, 0, ne * me, 1, 0, ne * me};
+        op->phase_begin(2);
+#define C3(N) launch_mid<N, true, false>(s, ne * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
+        LS3_DISPATCH(l, C3);
+        op->phase_end(); op->launches++;
+        LS_CUDA_TRY(e);
+    }
+    // P4: inverse y lines (sx,p): slots at A2[sx + ne*me*p + ne*sy]; out C1[sx + ne*m*p + ne*j]
+    {
+        LineAddr la{ne, 1, ne * me, ne, 1, ne * m, ne};
+        op->phase_begin(3);
+#define C4(N) launch_inv<N, true>(s, ne * l, op->d_A2, nullptr, op->d_A1, op->d_TABm, 1.0, la)
+        LS3_DISPATCH(m, C4);
+        op->phase_end(); op->launches++;
+        LS_CUDA_TRY(e);
+    }
+    // P5: inverse x lines + combine
+    {
+        LineAddr la{1L << 40, ne, 0, 1, n, 0, 1};
+        op->phase_begin(4);
+#define C5(N) launch_inv<N, false>(s, m * l, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
+        LS3_DISPATCH(n, C5);
+        op->phase_end(); op->launches++;
+        LS_CUDA_TRY(e);
+    }
+    return LS_OK;
+}
+
+}  // namespace
+
+int Op3D::apply_dev(const cd* b, cd* y, int mode) { return apply_device3(this, b, y, mode); }
+
+extern "C" {
+
+int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
+                   const double* nu, const ls_cdouble* gfft, double omega, double L, double Lp, int flags) {
+    (void)flags;
+    LS_REQUIRE(out && nu, LS_ERR_INVALID, "ls_op3d_create: null pointer");
+    LS_REQUIRE(n > 0 && m > 0 && l > 0, LS_ERR_INVALID, "ls_op3d_create: non-positive size");
+    LS_REQUIRE(ne == 4 * n && me == 4 * m && le == 4 * l, LS_ERR_INVALID,
+               "ls_op3d_create: Greengard_Vico needs ne = 4n, me = 4m, le = 4l (FastConvolution3D.jl:100)");
+    LS_REQUIRE(n == m, LS_ERR_INVALID,
+               "ls_op3d_create: FFTconvolution pads (ne, ne, le): n must equal m (FastConvolution3D.jl:48)");
+    auto ok3 = [](long v) { return v == 64 || v == 128 || v == 256 || v == 512; };
+    LS_REQUIRE(ok3(n) && ok3(m) && ok3(l), LS_ERR_UNSUPPORTED,
+               "ls_op3d_create: n=%ld m=%ld l=%ld - the GPU path serves powers of two in [64, 512]", (long)n, (long)m, (long)l);
+    LS_REQUIRE(gfft != nullptr || (L > 0 && Lp > 0), LS_ERR_INVALID,
+               "ls_op3d_create: pass GFFT or the Greengard-Vico parameters L, Lp to generate it on the device");
+
+    Op3D* op = new Op3D();
+    int rc = op->init_base(KIND_OP3D);
+    if (rc) { delete op; return rc; }
+    op->n = n; op->m = m; op->l = l; op->ne = ne; op->me = me; op->le = le; op->omega = omega;
+    const size_t N = (size_t)n * m * l, NE = (size_t)ne * me * le;
+#define TRY(x) do { rc = (x); if (rc) { delete op; return rc; } } while (0)
+    TRY(op->dupload((void**)&op->d_nu, nu, N * sizeof(double)));
+    {
+        auto Tn = engine_table((int)n), Tm = engine_table((int)m), Tl = engine_table((int)l);
+        TRY(op->dupload((void**)&op->d_TABn, Tn.data(), Tn.size() * sizeof(cd)));
+        TRY(op->dupload((void**)&op->d_TABm, Tm.data(), Tm.size() * sizeof(cd)));
+        TRY(op->dupload((void**)&op->d_TABl, Tl.data(), Tl.size() * sizeof(cd)));
+    }
+    {
+        auto fx = slot_freq((int)n), fy = slot_freq((int)m), fz = slot_freq((int)l);
+        int *d_fx = nullptr, *d_fy = nullptr, *d_fz = nullptr;
+        cd* d_gin = nullptr;
+        TRY(op->dupload((void**)&d_fx, fx.data(), fx.size() * sizeof(int)));
+        TRY(op->dupload((void**)&d_fy, fy.data(), fy.size() * sizeof(int)));
+        TRY(op->dupload((void**)&d_fz, fz.data(), fz.size() * sizeof(int)));
+        if (gfft) TRY(op->dupload((void**)&d_gin, gfft, NE * sizeof(cd)));
+        TRY(op->dmalloc((void**)&op->d_G, NE * sizeof(cd)));
+        GenParams p;
+        p.n = n; p.m = m; p.l = l; p.ne = ne; p.me = me; p.le = le;
+        p.dk = gfft ? 0.0 : 2.0 * 3.141592653589793 / Lp;
+        p.L = L; p.k = omega;
+        p.eLk_re = cos(L * omega); p.eLk_im = sin(L * omega);
+        p.scale = 1.0 / ((double)ne * (double)me * (double)le);
+        k_fill_g3d<<<148 * 16, 256, 0, op->stream>>>(d_gin, op->d_G, d_fx, d_fy, d_fz, p);
+        cudaError_t e = cudaStreamSynchronize(op->stream);
+        if (e != cudaSuccess) { set_error("spectrum setup failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
+        if (d_gin) op->dfree(d_gin);
+        op->dfree(d_fx); op->dfree(d_fy); op->dfree(d_fz);
+    }
+    TRY(op->dmalloc((void**)&op->d_A1, (size_t)ne * m * l * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_A2, (size_t)ne * me * l * sizeof(cd)));
+#undef TRY
+    *out = reinterpret_cast<ls_handle>(op);
+    return LS_OK;
+}
+
+int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc) {
+    LS_REQUIRE(h && b && y, LS_ERR_INVALID, "ls_op3d_apply: null argument");
+    Op3D* op = reinterpret_cast<Op3D*>(h);
+    LS_REQUIRE(op->kind == KIND_OP3D, LS_ERR_INVALID, "ls_op3d_apply: not a 3-D operator handle");
+    LS_REQUIRE(mode == LS_APPLY_FASTCONVOLUTION || mode == LS_APPLY_FFTCONVOLUTION, LS_ERR_INVALID,
+               "ls_op3d_apply: unknown mode %d", mode);
+    LS_CUDA_TRY(cudaSetDevice(op->device));
+    const size_t bytes = (size_t)op->n * op->m * op->l * sizeof(cd);
+    if (memloc == LS_MEM_DEVICE)
+        return apply_device3(op, reinterpret_cast<const cd*>(b), reinterpret_cast<cd*>(y), mode);
+    LS_REQUIRE(memloc == LS_MEM_HOST, LS_ERR_INVALID, "ls_op3d_apply: unknown memloc %d", memloc);
+    if (!op->d_b) {
+        int rc;
+        if ((rc = op->dmalloc((void**)&op->d_b, bytes))) return rc;
+        if ((rc = op->dmalloc((void**)&op->d_y, bytes))) return rc;
+    }
+    LS_CUDA_TRY(cudaMemcpyAsync(op->d_b, b, bytes, cudaMemcpyHostToDevice, op->stream));
+    int rc = apply_device3(op, op->d_b, op->d_y, mode);
+    if (rc) return rc;
+    LS_CUDA_TRY(cudaMemcpyAsync(y, op->d_y, bytes, cudaMemcpyDeviceToHost, op->stream));
+    LS_CUDA_TRY(cudaStreamSynchronize(op->stream));
+    return LS_OK;
+}
+
+}  // extern "C"

@@ -151,6 +151,74 @@ class FastM(_Handle):
         return Y
 
 
+class FastM3D(_Handle):
+    """``struct FastM3D`` (FastConvolution3D.jl:7-26) with the apply on the GPU.
+
+    ``GFFT`` is the (ne, me, le) centred spectrum as the reference holds it, or ``None`` together
+    with the Greengard-Vico parameters ``L`` and ``Lp`` (FastConvolution3D.jl:72-73) to have
+    Gtruncated3D evaluated on the device (the only practical way at 256^3 and above).
+    The reference defines only ``*`` for this type (Q4); ``mul_``, ``size`` and ``eltype`` are
+    added so that gmres! (which needs them) takes the operator.
+    """
+
+    def __init__(self, GFFT, nu, ne, me, le, n, m, l, k, quadRule="Greengard_Vico", L=None, Lp=None):
+        super().__init__()
+        self.ne, self.me, self.le, self.n, self.m, self.l = (int(v) for v in (ne, me, le, n, m, l))
+        self.omega = float(k)
+        self.quadRule = quadRule
+        if quadRule != "Greengard_Vico":
+            raise ValueError("FastM3D only knows quadRule='Greengard_Vico' (FastConvolution3D.jl:70)")
+        nu = np.ascontiguousarray(np.asarray(nu, dtype=np.float64).reshape(-1))
+        self.N = self.n * self.m * self.l
+        if nu.shape[0] != self.N:
+            raise ValueError("DimensionMismatch: nu has %d entries, expected %d" % (nu.shape[0], self.N))
+        if GFFT is None:
+            if L is None or Lp is None:
+                raise ValueError("pass GFFT, or L and Lp to generate the Greengard-Vico spectrum on the device")
+            gp = None
+        else:
+            GFFT = np.asarray(GFFT)
+            if GFFT.shape != (self.ne, self.me, self.le):
+                raise ValueError("DimensionMismatch: GFFT is %s, expected %s" % (GFFT.shape, (self.ne, self.me, self.le)))
+            g = np.asfortranarray(GFFT.astype(np.complex128, copy=False))
+            gp = C.c_void_p(g.ctypes.data)
+        check(lib().ls_op3d_create(C.byref(self._h), self.n, self.m, self.l, self.ne, self.me, self.le, ptr(nu), gp,
+                                   self.omega, float(L or 0.0), float(Lp or 0.0), 0))
+
+    def size(self, dim=None):
+        if dim is not None:
+            return self.N
+        return ((self.N,), (self.N,))
+
+    def eltype(self):
+        return np.dtype(np.complex128)
+
+    def _apply(self, b, out, mode):
+        if isinstance(b, DeviceBuffer) or isinstance(out, DeviceBuffer):
+            if not (isinstance(b, DeviceBuffer) and isinstance(out, DeviceBuffer)):
+                raise TypeError("b and out must both be DeviceBuffer or both numpy arrays")
+            check(lib().ls_op3d_apply(self.handle, ptr(b), ptr(out), mode, _lib.MEM_DEVICE))
+            return out
+        b = _as_c128(b, self.N)
+        if out is None:
+            out = np.empty(self.N, dtype=np.complex128)
+        check(lib().ls_op3d_apply(self.handle, ptr(b), ptr(out), mode, _lib.MEM_HOST))
+        return out
+
+    def __mul__(self, b):
+        """``*(M::FastM3D, b)`` FastConvolution3D.jl:31-37."""
+        return self._apply(b, None, _lib.APPLY_FASTCONVOLUTION)
+
+    __matmul__ = __mul__
+
+    def mul_(self, Y, b):
+        if isinstance(Y, DeviceBuffer) or (isinstance(Y, np.ndarray) and Y.flags.c_contiguous and Y.dtype == np.complex128
+                                           and Y.shape == (self.N,)):
+            return self._apply(b, Y, _lib.APPLY_FASTCONVOLUTION)
+        Y[:] = self._apply(b, None, _lib.APPLY_FASTCONVOLUTION)
+        return Y
+
+
 def fastconvolution(M: FastM, b, out=None):
     """``fastconvolution(M, b)`` FastConvolution.jl:58-107:  b + omega^2 G (nu .* b)."""
     return M._apply(b, out, _lib.APPLY_FASTCONVOLUTION)

@@ -77,6 +77,19 @@ int ls_op2d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int
 /* size(M,dim) / eltype, FastConvolution.jl:31-41: writes N = n*m */
 int ls_op_size(ls_handle h, int64_t* N);
 
+/* ---- 3-D operator: struct FastM3D, FastConvolution3D.jl:7-26 ----------------------------- *
+ * GFFT (ne*me*le complex, column-major, centred ordering) may be NULL: the Greengard-Vico
+ * spectrum Gtruncated3D(L, k, |kappa|) (Functions.jl:49-51; grid kappa = (2 pi/Lp)(-2n:2n-1),
+ * FastConvolution3D.jl:72-99) is then evaluated on the device straight into the kernel layout
+ * (at 256^3 the array is 17 GB, at 512^3 137 GB - too big to ship from the host).
+ * Served: n == m (the reference pads (ne, ne, le), :48), n, m, l in {64,128,256,512}.        */
+int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
+                   const double* nu, const ls_cdouble* gfft_or_null, double omega, double L, double Lp,
+                   int flags);
+/* mode 0: `*(M::FastM3D, b)` = b + omega^2 FFTconvolution(M, nu.*b)  (FastConvolution3D.jl:31-37)
+ * mode 1: FFTconvolution(M, b)                                      (FastConvolution3D.jl:39-63) */
+int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc);
+
 /* ---- sparsifying matrix As: SparseMatrixCSC{ComplexF64,Int64}, preconditioner.jl:27-30 ------ *
  * Arrays exactly as Julia holds them (A.colptr, A.rowval, A.nzval; 1-based).  Converted once
  * to CSR/int32 on the device.                                                              */
