@@ -69,10 +69,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    link = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    link = [nvcc, "-shared", "--cudart", "shared", "-o", LIB] + objs
     nccl_dir = _nccl_libdir()
-    if nccl_dir and os.path.exists(os.path.join(CSRC, "op3d_dist.cu")):
+    if nccl_dir:
         link += ["-L" + nccl_dir, "-l:libnccl.so.2", "-Xlinker", "-rpath", "-Xlinker", nccl_dir]
+    else:
+        link += ["-lnccl"]
     p = subprocess.run(link, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))

@@ -93,14 +93,16 @@ k_dot(const cd* __restrict__ x, const cd* __restrict__ y, long n, double2* parti
     block_finish(sx, sy, partials, ticket, out_re, out_im, 0);
 }
 
+__global__ void k_sqrt1(double* v) { *v = sqrt(*v); }
+
 __global__ void __launch_bounds__(RED_THREADS)
-k_nrm2(const cd* __restrict__ x, long n, double2* partials, unsigned* ticket, double* out) {
+k_nrm2(const cd* __restrict__ x, long n, double2* partials, unsigned* ticket, double* out, int take_sqrt) {
     double sx = 0.0;
     for (long i = (long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long)gridDim.x * RED_THREADS) {
         const cd a = x[i];
         sx += a.x * a.x + a.y * a.y;
     }
-    block_finish(sx, 0.0, partials, ticket, out, nullptr, 1);
+    block_finish(sx, 0.0, partials, ticket, out, nullptr, take_sqrt);
 }
 
 // w -= h_prev * vprev ;  h = conj(vi) . w
@@ -126,7 +128,7 @@ k_axpy_dot(const cd* __restrict__ vprev, const double* hprev_re, const double* h
 // w -= h_prev * vprev ;  out = sqrt(sum |w|^2)
 __global__ void __launch_bounds__(RED_THREADS)
 k_axpy_nrm2(const cd* __restrict__ vprev, const double* hprev_re, const double* hprev_im, cd* w, long n,
-            double2* partials, unsigned* ticket, double* out) {
+            double2* partials, unsigned* ticket, double* out, int take_sqrt) {
     const double hr = *hprev_re, hi = *hprev_im;
     double sx = 0.0;
     for (long i = (long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long)gridDim.x * RED_THREADS) {
@@ -137,7 +139,7 @@ k_axpy_nrm2(const cd* __restrict__ vprev, const double* hprev_re, const double* 
         w[i] = ww;
         sx += ww.x * ww.x + ww.y * ww.y;
     }
-    block_finish(sx, 0.0, partials, ticket, out, nullptr, 1);
+    block_finish(sx, 0.0, partials, ticket, out, nullptr, take_sqrt);
 }
 
 // y += alpha*x  (alpha by value)
@@ -207,32 +209,51 @@ struct Krylov : HandleBase {
 
     int grid_stream(long nn) const { long b = (nn + 255) / 256; return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16); }
 
-    int dot(const cd* x, const cd* y, double* out2, cudaStream_t s) {
-        k_dot<<<RED_BLOCKS, RED_THREADS, 0, s>>>(x, y, n, d_partials, d_ticket, out2, out2 + 1);
+    // sharded vectors (z slabs, one process per GPU): local sums are all-reduced as scalars
+    ncclComm_t comm = nullptr;
+    int allreduce(double* v, int count, cudaStream_t s) {
+        if (!comm) return LS_OK;
+        ncclResult_t r = ncclAllReduce(v, v, count, ncclDouble, ncclSum, comm, s);
+        if (r != ncclSuccess) { set_error("ncclAllReduce failed: %s", ncclGetErrorString(r)); return LS_ERR_NCCL; }
+        return LS_OK;
+    }
+    int finish_norm(double* v, cudaStream_t s) {
+        if (!comm) return LS_OK;
+        int rc = allreduce(v, 1, s);
+        if (rc) return rc;
+        k_sqrt1<<<1, 1, 0, s>>>(v);
         launches++;
         return LS_OK;
     }
-    int nrm2(const cd* x, double* out, cudaStream_t s) {
-        k_nrm2<<<RED_BLOCKS, RED_THREADS, 0, s>>>(x, n, d_partials, d_ticket, out);
+    int dot(const cd* x, const cd* y, double* out2, cudaStream_t s) {
+        k_dot<<<RED_BLOCKS, RED_THREADS, 0, s>>>(x, y, n, d_partials, d_ticket, out2, out2 + 1);
         launches++;
-        return LS_OK;
+        return allreduce(out2, 2, s);
+    }
+    int nrm2(const cd* x, double* out, cudaStream_t s) {
+        k_nrm2<<<RED_BLOCKS, RED_THREADS, 0, s>>>(x, n, d_partials, d_ticket, out, comm ? 0 : 1);
+        launches++;
+        return finish_norm(out, s);
     }
     // modified Gram-Schmidt of w against V[:,0..k-1] and normalisation; h (k+1 complex) lands in d_scal
     int mgs(const cd* V, long ldv, int k, cd* w, cudaStream_t s) {
         double* h = d_scal;
+        int rc;
         if (k == 0) {
-            nrm2(w, h, s);
+            if ((rc = nrm2(w, h, s))) return rc;
             cudaMemsetAsync(h + 1, 0, sizeof(double), s);
         } else {
-            dot(V, w, h, s);
+            if ((rc = dot(V, w, h, s))) return rc;
             for (int i = 1; i < k; ++i) {
                 k_axpy_dot<<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(i - 1) * ldv, h + 2 * (i - 1), h + 2 * (i - 1) + 1,
                                                               V + (long)i * ldv, w, n, d_partials, d_ticket, h + 2 * i, h + 2 * i + 1);
                 launches++;
+                if ((rc = allreduce(h + 2 * i, 2, s))) return rc;
             }
             k_axpy_nrm2<<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(k - 1) * ldv, h + 2 * (k - 1), h + 2 * (k - 1) + 1, w, n,
-                                                           d_partials, d_ticket, h + 2 * k);
+                                                           d_partials, d_ticket, h + 2 * k, comm ? 0 : 1);
             launches++;
+            if ((rc = finish_norm(h + 2 * k, s))) return rc;
             cudaMemsetAsync(h + 2 * k + 1, 0, sizeof(double), s);
         }
         k_scal_inv_dev<<<grid_stream(n), 256, 0, s>>>(h + 2 * k, w, n);
@@ -365,7 +386,7 @@ int ls_mgs_step(ls_handle h, const ls_cdouble* V, int64_t ldv, int k, ls_cdouble
     KRYLOV_HANDLE(K, h, "ls_mgs_step");
     LS_REQUIRE(V && w && hcol, LS_ERR_INVALID, "ls_mgs_step: null pointer");
     LS_REQUIRE(k >= 0 && k <= 64 && ldv >= K->n, LS_ERR_INVALID, "ls_mgs_step: k must be in [0,64] and ldv >= n");
-    K->mgs((const cd*)V, ldv, k, (cd*)w, K->stream);
+    { int rc = K->mgs((const cd*)V, ldv, k, (cd*)w, K->stream); if (rc) return rc; }
     LS_CUDA_TRY(cudaGetLastError());
     LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, 2 * (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, K->stream));
     LS_CUDA_TRY(cudaStreamSynchronize(K->stream));
@@ -386,11 +407,14 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
     if (As) LS_REQUIRE(As->kind == KIND_SPM && As->nrows == K->n && As->ncols == K->n, LS_ERR_INVALID,
                        "ls_gmres: As must be an N x N sparse-matrix handle");
     const long n = K->n;
-    if (restart <= 0) restart = (int)(n < 20 ? n : 20);
+    if (restart <= 0) restart = 20;
     LS_REQUIRE(restart <= 64, LS_ERR_UNSUPPORTED, "ls_gmres: restart > 64 is not supported");
-    if (maxiter <= 0) maxiter = n;
+    if (maxiter <= 0) maxiter = n;     // callers with sharded vectors pass the global N
     // all work is enqueued on the operator's stream so that its apply orders with our kernels
     cudaStream_t s = op->stream;
+    K->comm = op->nccl_comm();      // sharded operator: dots / norms are all-reduced on its communicator
+    LS_REQUIRE(!(K->comm && (As || msp_solve)), LS_ERR_UNSUPPORTED,
+               "ls_gmres: the preconditioner is not sharded (SURVEY.md section 8(e)); use Pl = Identity with a sharded operator");
     const size_t vb = (size_t)n * sizeof(cd);
     if (K->v_cols < restart + 1) {
         if (K->d_V) K->dfree(K->d_V);
@@ -456,7 +480,8 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
         }
         int rc = precond(V);
         if (rc) return rc;
-        K->nrm2(V, K->d_scal, s);
+        rc = K->nrm2(V, K->d_scal, s);
+        if (rc) return rc;
         k_scal_inv_dev<<<gs, 256, 0, s>>>(K->d_scal, V, n);
         K->launches++;
         LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -486,7 +511,8 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
         if (rc) return rc;
         mv++;
         // orthogonalize_and_normalize! (modified Gram-Schmidt), Hessenberg column -> host
-        K->mgs(V, ldv, k, w, s);
+        rc = K->mgs(V, ldv, k, w, s);
+        if (rc) return rc;
         LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, 2 * (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
         LS_CUDA_TRY(cudaStreamSynchronize(s));
         for (int i = 0; i <= k; ++i) H[i + (size_t)(k - 1) * ldh] = {K->h_scal[2 * i], K->h_scal[2 * i + 1]};

@@ -71,7 +71,14 @@ struct LineAddr {
     long ldim0;
     long in_ls0, in_ls1, in_es;
     long out_ls0, out_ls1, out_es;
+    // slab split of the 4N-slot axis (multi-GPU transposes): slot s lives at
+    // (s & (2^shift - 1))*es + (s >> shift)*split_stride.  shift = 62 disables it.
+    int split_shift = 62;
+    long split_stride = 0;
 };
+__device__ __forceinline__ long slot_off(const LineAddr& a, long s, long es) {
+    return (s & ((1L << a.split_shift) - 1)) * es + (s >> a.split_shift) * a.split_stride;
+}
 __device__ __forceinline__ long line_in(const LineAddr& a, long L) { return (L % a.ldim0) * a.in_ls0 + (L / a.ldim0) * a.in_ls1; }
 __device__ __forceinline__ long line_out(const LineAddr& a, long L) { return (L % a.ldim0) * a.out_ls0 + (L / a.ldim0) * a.out_ls1; }
 
@@ -122,9 +129,9 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
 #pragma unroll
         for (int a = 0; a < E; ++a) v[a] = x[a];
         fft_fwd<N>(v, t, r, ex, mp.lay, tw);
-        cd* o = out + out_base + (long)(r * N + t) * out_es;
+        cd* o = out + out_base;
 #pragma unroll
-        for (int e = 0; e < E; ++e) o[(long)(T * e) * out_es] = v[e];
+        for (int e = 0; e < E; ++e) o[slot_off(la, (long)(r * N + t + T * e), out_es)] = v[e];
         __syncthreads();   // next forward rewrites the exchange buffer at other addresses
     }
 }
@@ -238,9 +245,9 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __res
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
         cd v[E];
-        const cd* p = in + in_base + (long)(r * N + t) * la.in_es;
+        const cd* p = in + in_base;
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = p[(long)(T * e) * la.in_es];
+        for (int e = 0; e < E; ++e) v[e] = p[slot_off(la, (long)(r * N + t + T * e), la.in_es)];
         fft_inv<N>(v, t, r, ex, mp.lay, tw);
         demod_accumulate<N>(acc, v, r);
         __syncthreads();

@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../include/ls_cuda.h"
 #include "fft_engine.cuh"
+#include <nccl.h>
 
 namespace ls {
 
@@ -53,6 +54,9 @@ struct HandleBase {
         set_error("handle is not an operator");
         return LS_ERR_INVALID;
     }
+
+    // sharded operators expose their communicator so that Krylov reductions can all-reduce on it
+    virtual ncclComm_t nccl_comm() const { return nullptr; }
 
     // optional per-phase CUDA-event profiling (bench roofline of the dominant kernel)
     bool profiling = false;

@@ -7,8 +7,17 @@
 //   P4 k_inv_pruned<m,B>  y lines                 A2               -> C1 [ne m l]   (reuses A1)
 //   P5 k_inv_pruned<n,A>  x lines + combine       C1, b            -> y
 // Algorithmic HBM bytes per apply: 2360*N; the spectrum read is 1024*N of it.
+//
+// Multi-GPU (one process per GPU, P = 2/4/8 ranks): the grid is split into z slabs (l/P planes per
+// rank, a contiguous range of the vector).  P1 runs on the local planes and writes its output
+// already grouped by destination rank; one NCCL all-to-all re-slabs the (most pruned) ne x m x l
+// array along the x-slot axis; P2-P4 run on the rank's ne/P x-slots against its slab of the
+// spectrum; a second all-to-all brings the result back to z slabs for P5.  Neither exchange needs
+// a pack or unpack pass: both sides read/write the exchange buffers in place (slot_off()).
+// All-to-all volume per rank and direction: 16*4N*(P-1)/P^2 bytes.
 #include "ls_common.cuh"
 #include "line_kernels.cuh"
+#include "dist.cuh"
 
 using namespace ls;
 using namespace lsk;
@@ -17,19 +26,26 @@ namespace {
 
 struct Op3D : HandleBase {
     long n = 0, m = 0, l = 0, ne = 0, me = 0, le = 0;
+    int P = 1, rank = 0;
+    long nel = 0, lloc = 0;            // x-slots / z-planes owned by this rank
+    ncclComm_t comm = nullptr;
     double omega = 0;
-    double* d_nu = nullptr;
-    cd* d_G = nullptr;                 // [unit = (sx + ne*sy)/8][rz][slot_z][8]  scaled by 1/(ne me le)
+    double* d_nu = nullptr;            // local z slab
+    cd* d_G = nullptr;                 // [unit = (sxl + nel*sy)/8][rz][slot_z][8]  scaled by 1/(ne me le)
     cd *d_TABn = nullptr, *d_TABm = nullptr, *d_TABl = nullptr;
-    cd* d_A1 = nullptr;                // ne x m x l   (also C1)
-    cd* d_A2 = nullptr;                // ne x me x l
-    cd* d_b = nullptr; cd* d_y = nullptr; cd* d_tmp = nullptr;
-    int64_t op_size() const override { return n * m * l; }
+    cd* d_A1 = nullptr;                // P1 output / P5 input: [dest rank][nel][m][lloc]   (= ne x m x l when P == 1)
+    cd* d_A1T = nullptr;               // re-slabbed: nel x m x l  (P > 1 only)
+    cd* d_A2 = nullptr;                // nel x me x l
+    cd* d_b = nullptr; cd* d_y = nullptr;
+    int64_t op_size() const override { return n * m * lloc; }
     int apply_dev(const cd* b, cd* y, int mode) override;
+    ncclComm_t nccl_comm() const override { return comm; }
+    ~Op3D() override { if (comm) ncclCommDestroy(comm); }
 };
 
 struct GenParams {
     long n, m, l, ne, me, le;
+    long nel, sx0;      // x-slot slab of this rank
     double dk;          // 2 pi / Lp
     double L, k;        // truncation radius, wave number
     double eLk_re, eLk_im;
@@ -59,7 +75,7 @@ __device__ __forceinline__ cd gtrunc3d(double s, const GenParams& p) {
 // array `gin` (ne x me x le, centred) or by evaluating the Greengard-Vico formula.
 __global__ void k_fill_g3d(const cd* __restrict__ gin, cd* __restrict__ gout, const int* __restrict__ fx,
                            const int* __restrict__ fy, const int* __restrict__ fz, GenParams p) {
-    const long total = p.ne * p.me * p.le;
+    const long total = p.nel * p.me * p.le;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long lam = idx & 7;
         long q = idx >> 3;
@@ -67,7 +83,7 @@ __global__ void k_fill_g3d(const cd* __restrict__ gin, cd* __restrict__ gout, co
         const long rz = q & 3;
         const long unit = q >> 2;
         const long Lidx = unit * 8 + lam;
-        const long sx = Lidx % p.ne, sy = Lidx / p.ne;
+        const long sx = p.sx0 + Lidx % p.nel, sy = Lidx / p.nel;
         const long kx = 4L * fx[sx % p.n] + sx / p.n;
         const long ky = 4L * fy[sy % p.m] + sy / p.m;
         const long kz = 4L * fz[sz] + rz;
@@ -95,52 +111,89 @@ __global__ void k_fill_g3d(const cd* __restrict__ gin, cd* __restrict__ gout, co
         default: set_error("unsupported 3-D size %ld", (long)(N_)); return LS_ERR_UNSUPPORTED; \
     }
 
+// all-to-all of equal contiguous blocks (grouped ncclSend/ncclRecv over NVLink)
+int all_to_all(Op3D* op, const cd* send, cd* recv, long blk_elems) {
+    ncclResult_t r = ncclGroupStart();
+    for (int q = 0; q < op->P && r == ncclSuccess; ++q) {
+        r = ncclSend(send + (long)q * blk_elems, (size_t)blk_elems * 2, ncclDouble, q, op->comm, op->stream);
+        if (r == ncclSuccess)
+            r = ncclRecv(recv + (long)q * blk_elems, (size_t)blk_elems * 2, ncclDouble, q, op->comm, op->stream);
+    }
+    ncclResult_t r2 = ncclGroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) {
+        set_error("NCCL all-to-all failed: %s", ncclGetErrorString(r));
+        return LS_ERR_NCCL;
+    }
+    return LS_OK;
+}
+
 int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     cudaError_t e = cudaSuccess;
     cudaStream_t s = op->stream;
-    const long n = op->n, m = op->m, l = op->l, ne = op->ne, me = op->me;
+    const long n = op->n, m = op->m, l = op->l, me = op->me, nel = op->nel, lloc = op->lloc;
     const bool full = (mode == LS_APPLY_FASTCONVOLUTION);
-    // P1: x lines (j,p): in b[n*(j + m p) + i]; out A1[ne*(j + m p) + sx]
+    const long blk = nel * m * lloc;                 // elements exchanged with each peer
+    int shift = 0;
+    while ((1L << shift) < nel) ++shift;
+    // P1: x lines (j, p_loc): in b[n*line + i]; slot sx -> block sx/nel, A1[(sx/nel)*blk + nel*line + sx%nel]
     {
-        LineAddr la{1L << 40, n, 0, 1, ne, 0, 1};
+        LineAddr la{1L << 40, n, 0, 1, nel, 0, 1};
+        la.split_shift = shift; la.split_stride = blk;
         op->phase_begin(0);
-#define C1(N) launch_fwd<N, false>(s, m * l, b, full ? op->d_nu : nullptr, op->d_A1, op->d_TABn, la)
+#define C1(N) launch_fwd<N, false>(s, m * lloc, b, full ? op->d_nu : nullptr, op->d_A1, op->d_TABn, la)
         LS3_DISPATCH(n, C1);
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
-    // P2: y lines (sx,p): in A1[sx + ne*m*p + ne*j]; out A2[sx + ne*me*p + ne*sy]
+    const cd* a1t = op->d_A1;
+    if (op->P > 1) {
+        op->phase_begin(5);
+        int rc = all_to_all(op, op->d_A1, op->d_A1T, blk);
+        op->phase_end();
+        if (rc) return rc;
+        a1t = op->d_A1T;
+    }
+    cd* c1t = (op->P > 1) ? op->d_A1T : op->d_A1;
+    // P2: y lines (sxl, p): in A1T[sxl + nel*m*p + nel*j]; out A2[sxl + nel*me*p + nel*sy]
     {
-        LineAddr la{ne, 1, ne * m, ne, 1, ne * me, ne};
+        LineAddr la{nel, 1, nel * m, nel, 1, nel * me, nel};
         op->phase_begin(1);
-#define C2(N) launch_fwd<N, true>(s, ne * l, op->d_A1, nullptr, op->d_A2, op->d_TABm, la)
+#define C2(N) launch_fwd<N, true>(s, nel * l, a1t, nullptr, op->d_A2, op->d_TABm, la)
         LS3_DISPATCH(m, C2);
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
-    // P3: z lines L = sx + ne*sy: point p at A2[L + ne*me*p], in place
+    // P3: z lines L = sxl + nel*sy: point p at A2[L + nel*me*p], in place
     {
-        LineAddr la{1L << 40, 1, 0, ne * me, 1, 0, ne * me};
+        LineAddr la{1L << 40, 1, 0, nel * me, 1, 0, nel * me};
         op->phase_begin(2);
-#define C3(N) launch_mid<N, true, false>(s, ne * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
+#define C3(N) launch_mid<N, true, false>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
         LS3_DISPATCH(l, C3);
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
-    // P4: inverse y lines (sx,p): slots at A2[sx + ne*me*p + ne*sy]; out C1[sx + ne*m*p + ne*j]
+    // P4: inverse y lines (sxl, p): slots at A2[sxl + nel*me*p + nel*sy]; out C1T[sxl + nel*m*p + nel*j]
     {
-        LineAddr la{ne, 1, ne * me, ne, 1, ne * m, ne};
+        LineAddr la{nel, 1, nel * me, nel, 1, nel * m, nel};
         op->phase_begin(3);
-#define C4(N) launch_inv<N, true>(s, ne * l, op->d_A2, nullptr, op->d_A1, op->d_TABm, 1.0, la)
+#define C4(N) launch_inv<N, true>(s, nel * l, op->d_A2, nullptr, c1t, op->d_TABm, 1.0, la)
         LS3_DISPATCH(m, C4);
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
-    // P5: inverse x lines + combine
+    if (op->P > 1) {
+        op->phase_begin(6);
+        int rc = all_to_all(op, op->d_A1T, op->d_A1, blk);
+        op->phase_end();
+        if (rc) return rc;
+    }
+    // P5: inverse x lines + combine; slot sx of line (j, p_loc) at A1[(sx/nel)*blk + nel*line + sx%nel]
     {
-        LineAddr la{1L << 40, ne, 0, 1, n, 0, 1};
+        LineAddr la{1L << 40, nel, 0, 1, n, 0, 1};
+        la.split_shift = shift; la.split_stride = blk;
         op->phase_begin(4);
-#define C5(N) launch_inv<N, false>(s, m * l, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
+#define C5(N) launch_inv<N, false>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
         LS3_DISPATCH(n, C5);
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
@@ -148,15 +201,9 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     return LS_OK;
 }
 
-}  // namespace
-
-int Op3D::apply_dev(const cd* b, cd* y, int mode) { return apply_device3(this, b, y, mode); }
-
-extern "C" {
-
-int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
-                   const double* nu, const ls_cdouble* gfft, double omega, double L, double Lp, int flags) {
-    (void)flags;
+int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
+             const double* nu, const ls_cdouble* gfft, double omega, double L, double Lp,
+             int rank, int nranks, const void* nccl_id) {
     LS_REQUIRE(out && nu, LS_ERR_INVALID, "ls_op3d_create: null pointer");
     LS_REQUIRE(n > 0 && m > 0 && l > 0, LS_ERR_INVALID, "ls_op3d_create: non-positive size");
     LS_REQUIRE(ne == 4 * n && me == 4 * m && le == 4 * l, LS_ERR_INVALID,
@@ -168,14 +215,33 @@ int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, 
                "ls_op3d_create: n=%ld m=%ld l=%ld - the GPU path serves powers of two in [64, 512]", (long)n, (long)m, (long)l);
     LS_REQUIRE(gfft != nullptr || (L > 0 && Lp > 0), LS_ERR_INVALID,
                "ls_op3d_create: pass GFFT or the Greengard-Vico parameters L, Lp to generate it on the device");
+    LS_REQUIRE(nranks == 1 || nranks == 2 || nranks == 4 || nranks == 8, LS_ERR_INVALID,
+               "ls_op3d_create_dist: nranks must be 1, 2, 4 or 8");
+    LS_REQUIRE(rank >= 0 && rank < nranks, LS_ERR_INVALID, "ls_op3d_create_dist: rank out of range");
+    LS_REQUIRE(nranks == 1 || nccl_id != nullptr, LS_ERR_INVALID, "ls_op3d_create_dist: null NCCL id");
+    LS_REQUIRE(nranks == 1 || gfft == nullptr, LS_ERR_UNSUPPORTED,
+               "ls_op3d_create_dist: the sharded operator generates its spectrum slab on the device (pass NULL, L, Lp)");
 
     Op3D* op = new Op3D();
     int rc = op->init_base(KIND_OP3D);
     if (rc) { delete op; return rc; }
     op->n = n; op->m = m; op->l = l; op->ne = ne; op->me = me; op->le = le; op->omega = omega;
-    const size_t N = (size_t)n * m * l, NE = (size_t)ne * me * le;
+    op->P = nranks; op->rank = rank; op->nel = ne / nranks; op->lloc = l / nranks;
+    if (nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t r = ncclCommInitRank(&op->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            set_error("ncclCommInitRank failed: %s", ncclGetErrorString(r));
+            op->comm = nullptr;
+            delete op;
+            return LS_ERR_NCCL;
+        }
+    }
+    const long nel = op->nel, lloc = op->lloc;
+    const size_t Nloc = (size_t)n * m * lloc, NEloc = (size_t)nel * me * le;
 #define TRY(x) do { rc = (x); if (rc) { delete op; return rc; } } while (0)
-    TRY(op->dupload((void**)&op->d_nu, nu, N * sizeof(double)));
+    TRY(op->dupload((void**)&op->d_nu, nu, Nloc * sizeof(double)));
     {
         auto Tn = engine_table((int)n), Tm = engine_table((int)m), Tl = engine_table((int)l);
         TRY(op->dupload((void**)&op->d_TABn, Tn.data(), Tn.size() * sizeof(cd)));
@@ -189,10 +255,11 @@ int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, 
         TRY(op->dupload((void**)&d_fx, fx.data(), fx.size() * sizeof(int)));
         TRY(op->dupload((void**)&d_fy, fy.data(), fy.size() * sizeof(int)));
         TRY(op->dupload((void**)&d_fz, fz.data(), fz.size() * sizeof(int)));
-        if (gfft) TRY(op->dupload((void**)&d_gin, gfft, NE * sizeof(cd)));
-        TRY(op->dmalloc((void**)&op->d_G, NE * sizeof(cd)));
+        if (gfft) TRY(op->dupload((void**)&d_gin, gfft, (size_t)ne * me * le * sizeof(cd)));
+        TRY(op->dmalloc((void**)&op->d_G, NEloc * sizeof(cd)));
         GenParams p;
         p.n = n; p.m = m; p.l = l; p.ne = ne; p.me = me; p.le = le;
+        p.nel = nel; p.sx0 = (long)rank * nel;
         p.dk = gfft ? 0.0 : 2.0 * 3.141592653589793 / Lp;
         p.L = L; p.k = omega;
         p.eLk_re = cos(L * omega); p.eLk_im = sin(L * omega);
@@ -203,10 +270,38 @@ int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, 
         if (d_gin) op->dfree(d_gin);
         op->dfree(d_fx); op->dfree(d_fy); op->dfree(d_fz);
     }
-    TRY(op->dmalloc((void**)&op->d_A1, (size_t)ne * m * l * sizeof(cd)));
-    TRY(op->dmalloc((void**)&op->d_A2, (size_t)ne * me * l * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_A1, (size_t)ne * m * lloc * sizeof(cd)));
+    if (nranks > 1) TRY(op->dmalloc((void**)&op->d_A1T, (size_t)nel * m * l * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_A2, (size_t)nel * me * l * sizeof(cd)));
 #undef TRY
     *out = reinterpret_cast<ls_handle>(op);
+    return LS_OK;
+}
+
+}  // namespace
+
+int Op3D::apply_dev(const cd* b, cd* y, int mode) { return apply_device3(this, b, y, mode); }
+
+extern "C" {
+
+int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
+                   const double* nu, const ls_cdouble* gfft, double omega, double L, double Lp, int flags) {
+    (void)flags;
+    return create3d(out, n, m, l, ne, me, le, nu, gfft, omega, L, Lp, 0, 1, nullptr);
+}
+
+int ls_op3d_create_dist(ls_handle* out, int64_t n, int64_t m, int64_t l, const double* nu_slab, double omega,
+                        double L, double Lp, int rank, int nranks, const void* nccl_unique_id) {
+    return create3d(out, n, m, l, 4 * n, 4 * m, 4 * l, nu_slab, nullptr, omega, L, Lp, rank, nranks, nccl_unique_id);
+}
+
+int ls_nccl_unique_id(void* out128) {
+    LS_REQUIRE(out128, LS_ERR_INVALID, "ls_nccl_unique_id: null pointer");
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) { set_error("ncclGetUniqueId failed: %s", ncclGetErrorString(r)); return LS_ERR_NCCL; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, sizeof(id));
     return LS_OK;
 }
 
@@ -217,7 +312,7 @@ int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int
     LS_REQUIRE(mode == LS_APPLY_FASTCONVOLUTION || mode == LS_APPLY_FFTCONVOLUTION, LS_ERR_INVALID,
                "ls_op3d_apply: unknown mode %d", mode);
     LS_CUDA_TRY(cudaSetDevice(op->device));
-    const size_t bytes = (size_t)op->n * op->m * op->l * sizeof(cd);
+    const size_t bytes = (size_t)op->n * op->m * op->lloc * sizeof(cd);
     if (memloc == LS_MEM_DEVICE)
         return apply_device3(op, reinterpret_cast<const cd*>(b), reinterpret_cast<cd*>(y), mode);
     LS_REQUIRE(memloc == LS_MEM_HOST, LS_ERR_INVALID, "ls_op3d_apply: unknown memloc %d", memloc);

@@ -1,0 +1,99 @@
+"""One-process-per-GPU plumbing for the slab-decomposed 3-D operator.
+
+torch.distributed is used only as the rendezvous (rank / world size, broadcasting the 128-byte
+NCCL id, barriers, max-over-ranks of timings); the data path - both FFT transposes and the scalar
+all-reduces of the Krylov dots - runs inside libls_cuda.so on its own NCCL communicator.
+
+Sharding: rank r of P owns the z planes [r*l/P, (r+1)*l/P) of the
+n x m x l grid, i.e. the contiguous range [r*N/P, (r+1)*N/P) of every grid vector.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceBuffer, check, lib, ptr
+from .operators import FastM3D, _Handle, _as_c128
+
+
+def env_rank():
+    """(rank, world_size, local_rank) from the torchrun environment."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def slab_range(l, rank, nranks):
+    """z planes owned by `rank` (equal slabs; l must be divisible by nranks)."""
+    if l % nranks:
+        raise ValueError("l=%d is not divisible by the number of ranks %d" % (l, nranks))
+    lloc = l // nranks
+    return rank * lloc, (rank + 1) * lloc
+
+
+def vector_range(n, m, l, rank, nranks):
+    """[start, stop) of this rank's part of a grid vector (x fastest, z slowest)."""
+    p0, p1 = slab_range(l, rank, nranks)
+    return n * m * p0, n * m * p1
+
+
+def scatter_vector(v, n, m, l, rank, nranks):
+    a, b = vector_range(n, m, l, rank, nranks)
+    return np.ascontiguousarray(v[a:b])
+
+
+def exchange_bytes_per_rank(n, m, l, nranks):
+    """Bytes each rank sends over NVLink per transpose: 16 * 4N * (P-1) / P^2."""
+    return 16 * 4 * n * m * l * (nranks - 1) // (nranks * nranks)
+
+
+def make_unique_id():
+    buf = (C.c_char * 128)()
+    check(lib().ls_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def broadcast_unique_id(rank, group=None):
+    """Rank 0 creates the NCCL id, everyone receives it through torch.distributed (gloo or nccl)."""
+    import torch.distributed as dist
+    obj = [make_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0, group=group)
+    if not (isinstance(obj[0], bytes) and len(obj[0]) == 128):
+        raise _lib.LSCudaError(_lib.LS_ERR_NCCL, "NCCL id broadcast failed")
+    return obj[0]
+
+
+class FastM3DSharded(_Handle):
+    """The FastM3D operator slab-decomposed over `nranks` GPUs (collective object: every rank
+    constructs it and calls each apply).  Vectors are this rank's z slab."""
+
+    def __init__(self, nu_slab, n, m, l, k, L, Lp, rank, nranks, unique_id):
+        super().__init__()
+        self.n, self.m, self.l = int(n), int(m), int(l)
+        self.ne, self.me, self.le = 4 * self.n, 4 * self.m, 4 * self.l
+        self.omega = float(k)
+        self.rank, self.nranks = int(rank), int(nranks)
+        a, b = vector_range(self.n, self.m, self.l, self.rank, self.nranks)
+        self.N = b - a                       # local length
+        self.N_global = self.n * self.m * self.l
+        nu_slab = np.ascontiguousarray(np.asarray(nu_slab, dtype=np.float64).reshape(-1))
+        if nu_slab.shape[0] != self.N:
+            raise ValueError("DimensionMismatch: nu slab has %d entries, expected %d" % (nu_slab.shape[0], self.N))
+        idbuf = C.create_string_buffer(unique_id, 128) if self.nranks > 1 else None
+        check(lib().ls_op3d_create_dist(C.byref(self._h), self.n, self.m, self.l, ptr(nu_slab), self.omega,
+                                        float(L), float(Lp), self.rank, self.nranks, idbuf))
+
+    def size(self, dim=None):
+        if dim is not None:
+            return self.N
+        return ((self.N,), (self.N,))
+
+    def eltype(self):
+        return np.dtype(np.complex128)
+
+    _apply = FastM3D._apply
+    __mul__ = FastM3D.__mul__
+    __matmul__ = FastM3D.__mul__
+    mul_ = FastM3D.mul_

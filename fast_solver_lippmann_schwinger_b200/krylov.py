@@ -185,7 +185,7 @@ def gmres_(x, A, b, Pl=None, abstol=0.0, reltol=None, restart=None, maxiter=None
     N = A.size(1)
     reltol = float(np.sqrt(np.finfo(np.float64).eps)) if reltol is None else float(reltol)
     restart = min(20, N) if restart is None else int(restart)
-    maxiter = N if maxiter is None else int(maxiter)
+    maxiter = getattr(A, "N_global", N) if maxiter is None else int(maxiter)
     ws = workspace if workspace is not None else KrylovWorkspace(N)
     dev = isinstance(x, DeviceBuffer)
     if dev != isinstance(b, DeviceBuffer):

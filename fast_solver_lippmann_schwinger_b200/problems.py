@@ -46,3 +46,12 @@ def gv_problem_2d(n, m=None, ppw=10.0, a=1.0, nu=nu_gaussian_2d):
     X = np.repeat(x[:, None], m, axis=1).reshape(-1, order="F")
     Y = np.repeat(y[None, :], n, axis=0).reshape(-1, order="F")
     return np.asarray(nu(X, Y), dtype=np.float64), gv_spectrum_2d(n, m, h, k), k, h
+
+
+def nu_gaussian_3d_grid(n, a=1.0):
+    """examples/example3D.jl:43 on the n^3 grid x = -a/2:h:a/2-h (flattened, x fastest)."""
+    h = a / n
+    x = -a / 2 + h * np.arange(n)
+    g = np.exp(-40 * x ** 2) * (np.abs(x) < 0.48)
+    nu = 0.3 * g[:, None, None] * g[None, :, None] * g[None, None, :]
+    return np.ascontiguousarray(nu.reshape(-1, order="F"))

@@ -86,6 +86,16 @@ int ls_op_size(ls_handle h, int64_t* N);
 int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
                    const double* nu, const ls_cdouble* gfft_or_null, double omega, double L, double Lp,
                    int flags);
+/* Sharded 3-D operator, one process per GPU (P = 2, 4 or 8 ranks of one NVLink/NVSwitch box).
+ * Rank r owns the z planes [r*l/P, (r+1)*l/P): nu_slab, and the b / y of ls_op3d_apply, are that
+ * contiguous range of n*m*l/P values.  The padded FFT is slab-decomposed; its two transposes are
+ * NCCL all-to-alls on the communicator created here from `nccl_unique_id` (128 bytes obtained
+ * with ls_nccl_unique_id on rank 0 and broadcast by the host: torch.distributed / MPI /
+ * Distributed.jl).  Collective: every rank must call create and each apply.                   */
+int ls_nccl_unique_id(void* out128);
+int ls_op3d_create_dist(ls_handle* out, int64_t n, int64_t m, int64_t l, const double* nu_slab,
+                        double omega, double L, double Lp, int rank, int nranks,
+                        const void* nccl_unique_id);
 /* mode 0: `*(M::FastM3D, b)` = b + omega^2 FFTconvolution(M, nu.*b)  (FastConvolution3D.jl:31-37)
  * mode 1: FFTconvolution(M, b)                                      (FastConvolution3D.jl:39-63) */
 int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc);

@@ -1,0 +1,92 @@
+"""Worker run under torchrun by the multi-rank tests.
+
+    mode "cpu": gloo rendezvous, host-side sharding logic only (no CUDA)
+    mode "gpu": NCCL path - sharded 3-D apply and sharded GMRES checked against the CPU oracle
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    mode = sys.argv[1]
+    import torch.distributed as dist
+    import fast_solver_lippmann_schwinger_b200 as ls
+    from fast_solver_lippmann_schwinger_b200 import dist as lsd
+    rank, world, local = lsd.env_rank()
+    dist.init_process_group("gloo")
+    uid = lsd.broadcast_unique_id(rank)
+    ids = [None] * world
+    dist.all_gather_object(ids, uid)
+    assert all(i == ids[0] for i in ids) and len(uid) == 128
+
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    l = n
+    a, b_ = lsd.vector_range(n, n, l, rank, world)
+    ranges = [None] * world
+    dist.all_gather_object(ranges, (a, b_))
+    assert ranges[0][0] == 0 and ranges[-1][1] == n * n * l
+    assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    p0, p1 = lsd.slab_range(l, rank, world)
+    assert (p1 - p0) * n * n == b_ - a
+    assert lsd.exchange_bytes_per_rank(n, n, l, world) == 16 * 4 * n ** 3 * (world - 1) // world ** 2
+    if mode == "cpu":
+        # the sharded operator cannot be created without a GPU: it must fail loudly, not fall back
+        try:
+            lsd.FastM3DSharded(np.zeros(b_ - a), n, n, l, 1.0, 1.8, 4.0, rank, world, uid)
+            raise SystemExit("expected a CUDA/NCCL error without a GPU")
+        except ls.LSCudaError:
+            pass
+        dist.barrier()
+        if rank == 0:
+            print("DIST_CPU_OK")
+        dist.destroy_process_group()
+        return
+
+    # ---- GPU path ----------------------------------------------------------------------
+    from oracle import ls_oracle as O
+    from oracle.gmres_is import gmres as gmres_oracle
+    from fast_solver_lippmann_schwinger_b200._lib import check, lib
+    check(lib().ls_set_device(local))
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    x = -0.5 + h * np.arange(n)
+    Mo = O.buildFastConvolution3D(x, x, x, h, k, O.nu_gaussian_3d)
+    M = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid)
+    rng = np.random.default_rng(1234)
+    b = rng.standard_normal(n ** 3) + 1j * rng.standard_normal(n ** 3)
+    y_ref = Mo * b
+    y = M * np.ascontiguousarray(b[a:b_])
+    err = np.linalg.norm(y - y_ref[a:b_]) / np.linalg.norm(y_ref[a:b_])
+    errs = [None] * world
+    dist.all_gather_object(errs, float(err))
+    assert max(errs) <= 1e-12, errs
+    c_ref = O.FFTconvolution3D(Mo, b)
+    c = ls.FFTconvolution(M, np.ascontiguousarray(b[a:b_]))
+    assert np.linalg.norm(c - c_ref[a:b_]) / np.linalg.norm(c_ref[a:b_]) <= 1e-12
+
+    # sharded GMRES (dots all-reduced as scalars) against the oracle history
+    X, Y, Z = O.grid3d(x, x, x)
+    u_inc = np.exp(1j * k * X)
+    rhs = -(Mo * u_inc - u_inc)                       # example3D.jl:71-72
+    xo = np.zeros(n ** 3, complex)
+    xo, hist_o, conv_o, mv_o = gmres_oracle(xo, lambda v: Mo * v, rhs, maxiter=40)
+    xs = np.zeros(b_ - a, complex)
+    xs, hg = ls.gmres_(xs, M, np.ascontiguousarray(rhs[a:b_]), maxiter=40, log=True)
+    assert hg.iters == len(hist_o) and hg.isconverged == conv_o
+    mrel = np.max(np.abs(hg["resnorm"] - hist_o) / hist_o)
+    assert mrel < 1e-8, mrel
+    assert np.linalg.norm(xs - xo[a:b_]) / np.linalg.norm(xo[a:b_]) < 1e-8
+    dist.barrier()
+    if rank == 0:
+        print("DIST_GPU_OK world=%d n=%d apply_err=%.2e gmres_iters=%d hist_rel=%.2e" % (world, n, max(errs), hg.iters, mrel))
+    M.destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
