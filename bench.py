@@ -156,14 +156,118 @@ def workload_config(n):
             "parallelism": "replica per GPU (2-D path does not shard)"}
 
 
+def bench_3d(args, ls, lsd, rank, world, local_rank, dist, peak, peak_src):
+    """3-D 256^3 apply, slab-decomposed over `world` GPUs (strong scaling; world == 1: one GPU)."""
+    from fast_solver_lippmann_schwinger_b200.problems import nu_gaussian_3d_grid
+    n = args.n3
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    N = n ** 3
+    uid = lsd.broadcast_unique_id(rank) if world > 1 else None
+    a, b_ = lsd.vector_range(n, n, n, rank, world)
+    nu = nu_gaussian_3d_grid(n)[a:b_]
+    M = lsd.FastM3DSharded(nu, n, n, n, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid)
+    rng = np.random.default_rng(4321 + rank)
+    b = rng.standard_normal(b_ - a) + 1j * rng.standard_normal(b_ - a)
+    db = ls.DeviceBuffer.from_host(b)
+    dy = ls.DeviceBuffer(b.nbytes)
+
+    def barrier():
+        M.sync()
+        if dist is not None:
+            dist.barrier()
+
+    steps = max(5, min(args.steps, 20))
+    for _ in range(3):
+        M.mul_(dy, db)
+    barrier()
+    M.profile_enable(True)
+    l0 = M.launch_count()
+    barrier()
+    M.timer_start()
+    for _ in range(steps):
+        M.mul_(dy, db)
+    ms = M.timer_stop()
+    barrier()
+    ph, cnt = M.profile_read(7)
+    M.profile_enable(False)
+    launches = M.launch_count() - l0
+    # end to end: host slabs in pinned memory
+    hb = ls.PinnedArray((b_ - a,)); hy = ls.PinnedArray((b_ - a,))
+    hb.array[:] = b
+    M._apply(hb.array, hy.array, 0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        M._apply(hb.array, hy.array, 0)
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    per = [p / max(c, 1) for p, c in zip(ph, cnt)]
+    ms_step = ms / steps
+    p3 = per[2]
+    alg_p3 = 1536.0 * N / world            # spectrum 1024N + padded slab read 256N + write 256N, per rank
+    out = {
+        "metric": "ls_operator_applies_per_s_3d", "value": steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "scaling": "strong" if world > 1 else "single", "ms_per_apply": ms_step, "grid": [n, n, n], "padded": [4 * n] * 3,
+        "workload": "3-D Greengard_Vico LS apply %d^3 (padded %d^3), spectrum generated on device, z-slab sharded over %d GPU(s)" % (n, 4 * n, world),
+        "gpu_launches": launches,
+        "phase_ms": {"P1_x_fwd": per[0], "P2_y_fwd": per[1], "P3_z_fused": per[2], "P4_y_inv": per[3], "P5_x_inv": per[4],
+                     "a2a_fwd": per[5], "a2a_back": per[6]},
+        "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P3: fused z-line FFT, spectrum multiply, inverse)", "achieved": alg_p3 / (p3 * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": alg_p3 / (p3 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_p3, "launch_ms": p3},
+        "apply_roofline": {"algorithmic_bytes_per_apply_per_gpu": 2360.0 * N / world,
+                           "frac": 2360.0 * N / world / (ms_step * 1e-3) / 1e9 / peak},
+        "e2e": {"value": 3 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * (b_ - a), "d2h_bytes_per_step": 16 * (b_ - a)},
+    }
+    if world > 1:
+        xb = lsd.exchange_bytes_per_rank(n, n, n, world)
+        a2a = 0.5 * (per[5] + per[6])
+        out["nvlink"] = {"bytes_sent_per_gpu_per_transpose": xb, "a2a_ms": a2a, "achieved_GBs": xb / (a2a * 1e-3) / 1e9,
+                         "peak_GBs": 770.0, "frac": xb / (a2a * 1e-3) / 1e9 / 770.0,
+                         "peak_source": "measured peer copy per direction (B200_PROFILING.md)"}
+    M.destroy()
+    return out
+
+
+def bench_gmres(args, ls, M, n, k, h, peak):
+    """GMRES(20) time to reltol 1e-8 on the 2-D workload (Pl = Identity), plane-wave right-hand side."""
+    N = n * n
+    x = -0.5 + h * np.arange(n)
+    X = np.repeat(x[:, None], n, axis=1).reshape(-1, order="F")
+    u_inc = np.exp(1j * k * X)
+    rhs = -(M * u_inc - u_inc)                                 # tests/plasma_example.jl:160-161
+    db = ls.DeviceBuffer.from_host(rhs)
+    dx = ls.DeviceBuffer.from_host(np.zeros(N, complex))
+    ws = ls.KrylovWorkspace(N)
+    ls.gmres_(dx, M, db, reltol=1e-8, maxiter=25, workspace=ws)            # warm-up (allocations, first launches)
+    dx = ls.DeviceBuffer.from_host(np.zeros(N, complex))
+    t0 = time.perf_counter()
+    _, hist = ls.gmres_(dx, M, db, reltol=1e-8, maxiter=args.gmres_maxiter, log=True, workspace=ws)
+    dt = time.perf_counter() - t0
+    it = max(hist.iters, 1)
+    alg_iter = (568.0 + 64.0 * 10.5 + 48.0 + 32.0) * N         # apply + fused MGS (avg k = 10.5) + normalise
+    return {"metric": "gmres_time_to_1e-8", "time_s": dt, "iters": hist.iters, "converged": hist.isconverged, "restart": 20,
+            "mv_products": hist.mvps, "ms_per_iter": 1e3 * dt / it, "final_rel_residual": float(hist["resnorm"][-1] / hist["resnorm"][0]) if hist.iters else None,
+            "preconditioner": "Identity (the Msp direct solve is host-side and out of scope, SURVEY.md H1)",
+            "algorithmic_bytes_per_iter": alg_iter, "hbm_frac": alg_iter / (dt / it) / 1e9 / peak}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--n", type=int, default=2048, help="2-D grid side")
+    ap.add_argument("--n3", type=int, default=256, help="3-D grid side")
+    ap.add_argument("--gmres-maxiter", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 3-D and GMRES sections")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -172,12 +276,13 @@ def main():
 
     if args.impl == "reference":
         if args.steps > 20:
-            args.steps = 20      # bounded sample: ~1-2 s of 8-core CPU work per apply at 2048^2
+            args.steps = 20      # bounded sample: ~1-2 s of host CPU work per apply at 2048^2
         run_reference(args, rank, world)
         return
 
     args.warmup = max(args.warmup, 3)
     import fast_solver_lippmann_schwinger_b200 as ls
+    from fast_solver_lippmann_schwinger_b200 import dist as lsd
     from fast_solver_lippmann_schwinger_b200._lib import check, lib
     from fast_solver_lippmann_schwinger_b200.problems import gv_problem_2d
 
@@ -188,6 +293,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     check(lib().ls_set_device(local_rank))
+    peak, peak_src = measured_peaks()
 
     n = args.n
     N = n * n
@@ -237,7 +343,6 @@ def main():
     for _ in range(e2e_steps):
         ls.fastconvolution(M, hb.array, out=hy.array)    # H2D b, 3 kernels, D2H y, synchronous
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     checksum = float(np.abs(hy.array).sum())
 
     # ---- max over ranks ---------------------------------------------------------------
@@ -247,8 +352,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
 
+    extras = {}
+    if not args.no_extras:
+        if rank == 0 and world == 1:
+            extras["gmres"] = bench_gmres(args, ls, M, n, k, h, peak)
+        barrier()
+        M.destroy()
+        del db, dy
+        extras["apply3d"] = bench_3d(args, ls, lsd, rank, world, local_rank, dist, peak, peak_src)
+    clocks = sampler.stop() if rank == 0 else None
+
     if rank == 0:
-        peak, peak_src = measured_peaks()
         value = world * args.steps / (ms * 1e-3)
         p2_ms = phase_ms[1] / max(phase_cnt[1], 1)
         alg_bytes_p2 = 384.0 * N          # A read 64N + spectrum 256N + C write 64N
@@ -264,8 +378,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: 4x forward FFT, spectrum multiply, inverse FFT per padded row)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_p2,
-                         "launch_ms": p2_ms},
+                         "traffic": 1.342e9 + 0.256e9, "traffic_source": "ncu --set full r1_b: dram read 1.342 GB + write 0.256 GB per launch (profiles/r1_b_k_mid_fused_2048.txt)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_p2, "launch_ms": p2_ms},
             "apply_roofline": {"algorithmic_bytes_per_apply": 568.0 * N, "achieved": 568.0 * N / (ms / args.steps * 1e-3) / 1e9,
                                "frac": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs":
                                    568.0 * N / (ms / args.steps * 1e-3) / 1e9 / 8000.0},
@@ -273,6 +387,7 @@ def main():
                          "P3_inv_columns": phase_ms[2] / max(phase_cnt[2], 1)},
             "checksum": checksum,
         }
+        line.update(extras)
         if not args.no_cpu_baseline:
             v, cores, napp = cpu_reference_apply_rate(n)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
