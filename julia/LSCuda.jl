@@ -1,0 +1,183 @@
+# LSCuda.jl - Julia host side of the B200-native Lippmann-Schwinger hot path.
+#
+# Drop-in for the reference's operator objects: the types below carry the same fields and the same
+# method table as `FastM` (src/FastConvolution.jl:11-154), `FastM3D` (src/FastConvolution3D.jl:7-63)
+# and `SparsifyingPreconditioner` (src/preconditioner.jl:27-58,132-170), but every apply ends in a
+# `ccall` into libls_cuda.so (include/ls_cuda.h).  `IterativeSolvers.gmres!(u, A, rhs, Pl=precond)`
+# (examples/example.jl:85) takes them unchanged because it only needs `mul!`, `size`, `eltype`
+# and `ldiv!`; `gmres_gpu!` additionally keeps the whole Krylov basis on the device.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The same C-ABI calls are
+# exercised by the Python/ctypes mirror (fast_solver_lippmann_schwinger_b200/), see INTEGRATION.md.
+module LSCuda
+
+using LinearAlgebra, SparseArrays
+import Base: *, \, size, eltype
+import LinearAlgebra: mul!, ldiv!
+
+const libls = get(ENV, "LS_CUDA_LIB", "libls_cuda.so")
+
+const LS_MEM_HOST, LS_MEM_DEVICE = Cint(0), Cint(1)
+const LS_QUAD = Dict("trapezoidal" => Cint(0), "Greengard_Vico" => Cint(1))
+
+struct LSCudaError <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    throw(LSCudaError(rc, unsafe_string(ccall((:ls_last_error, libls), Cstring, ()))))
+end
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(p::Ptr{Cvoid})
+        h = new(p)
+        finalizer(h -> (h.ptr != C_NULL && ccall((:ls_destroy, libls), Cint, (Ptr{Cvoid},), h.ptr); h.ptr = C_NULL), h)
+        return h
+    end
+end
+
+set_device(dev::Integer) = check(ccall((:ls_set_device, libls), Cint, (Cint,), dev))
+
+# ---------------------------------------------------------------------------------- FastM (2-D)
+struct GPUFastM
+    h::Handle
+    nu::Vector{Float64}
+    ne::Int64; me::Int64; n::Int64; m::Int64
+    omega::Float64
+    quadRule::String
+end
+
+"GPUFastM(GFFT, nu, ne, me, n, m, k; quadRule) - same constructor as FastM (FastConvolution.jl:24)."
+function GPUFastM(GFFT::Array{ComplexF64,2}, nu::Vector{Float64}, ne, me, n, m, k; quadRule::String="trapezoidal")
+    size(GFFT) == (ne, me) || throw(DimensionMismatch("GFFT is $(size(GFFT)), expected ($ne, $me)"))
+    length(nu) == n * m || throw(DimensionMismatch("nu has $(length(nu)) entries, expected $(n*m)"))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ls_op2d_create, libls), Cint,
+                (Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{ComplexF64}, Float64, Cint, Cint),
+                out, n, m, ne, me, nu, GFFT, Float64(k), LS_QUAD[quadRule], 0))
+    return GPUFastM(Handle(out[]), nu, ne, me, n, m, Float64(k), quadRule)
+end
+"Move an existing reference operator to the GPU."
+GPUFastM(M) = GPUFastM(M.GFFT, M.nu, M.ne, M.me, M.n, M.m, M.omega; quadRule=M.quadRule)
+
+size(M::GPUFastM, dim) = length(M.nu)                       # FastConvolution.jl:31-33
+size(M::GPUFastM) = (size(M.nu), size(M.nu))                # :35-37 (tuple of tuples, kept)
+eltype(M::GPUFastM) = ComplexF64                            # :39-41
+
+function apply!(y::StridedVector{ComplexF64}, M::GPUFastM, b::StridedVector{ComplexF64}, mode::Integer)
+    length(b) == length(M.nu) == length(y) || throw(DimensionMismatch("vector length"))
+    (stride(b, 1) == 1 && stride(y, 1) == 1) || throw(ArgumentError("unit stride required"))
+    check(ccall((:ls_op2d_apply, libls), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Cint),
+                M.h.ptr, b, y, mode, LS_MEM_HOST))
+    return y
+end
+fastconvolution(M::GPUFastM, b::AbstractVector{ComplexF64}) = apply!(similar(b, ComplexF64), M, b, 0)   # :58-107
+FFTconvolution(M::GPUFastM, b::Vector{ComplexF64}) = apply!(similar(b), M, b, 1)                        # :110-154
+*(M::GPUFastM, b::AbstractVector{ComplexF64}) = fastconvolution(M, b)                                   # :43-48
+mul!(Y::AbstractVector{ComplexF64}, M::GPUFastM, b::AbstractVector{ComplexF64}) = apply!(Y, M, b, 0)    # :50-54
+
+# -------------------------------------------------------------------------------- FastM3D (3-D)
+struct GPUFastM3D
+    h::Handle
+    nu::Vector{Float64}
+    ne::Int64; me::Int64; le::Int64; n::Int64; m::Int64; l::Int64
+    omega::Float64
+    quadRule::String
+end
+
+"GFFT === nothing: the Greengard-Vico spectrum is generated on the device from (L, Lp) (FastConvolution3D.jl:72-99)."
+function GPUFastM3D(GFFT, nu::Vector{Float64}, ne, me, le, n, m, l, k; L=0.0, Lp=0.0, quadRule="Greengard_Vico")
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    g = GFFT === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(GFFT)
+    GC.@preserve GFFT check(ccall((:ls_op3d_create, libls), Cint,
+                (Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{ComplexF64}, Float64, Float64, Float64, Cint),
+                out, n, m, l, ne, me, le, nu, g, Float64(k), Float64(L), Float64(Lp), 0))
+    return GPUFastM3D(Handle(out[]), nu, ne, me, le, n, m, l, Float64(k), quadRule)
+end
+size(M::GPUFastM3D, dim) = length(M.nu)       # not defined upstream (Q4) - required by gmres!
+size(M::GPUFastM3D) = (size(M.nu), size(M.nu))
+eltype(M::GPUFastM3D) = ComplexF64
+function apply!(y::StridedVector{ComplexF64}, M::GPUFastM3D, b::StridedVector{ComplexF64}, mode::Integer)
+    check(ccall((:ls_op3d_apply, libls), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Cint),
+                M.h.ptr, b, y, mode, LS_MEM_HOST))
+    return y
+end
+*(M::GPUFastM3D, b::Array{ComplexF64,1}; verbose::Bool=false) = apply!(similar(b), M, b, 0)     # FastConvolution3D.jl:31-37
+FFTconvolution(M::GPUFastM3D, b::Array{ComplexF64,1}; verbose::Bool=false) = apply!(similar(b), M, b, 1)   # :39-63
+mul!(Y::AbstractVector{ComplexF64}, M::GPUFastM3D, b::AbstractVector{ComplexF64}) = apply!(Y, M, b, 0)
+
+# ---------------------------------------------------------------- sparsifying preconditioner
+struct GPUSparseMatrixCSC
+    h::Handle
+    m::Int64; n::Int64
+end
+function GPUSparseMatrixCSC(A::SparseMatrixCSC{ComplexF64,Int64})
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ls_spm_create, libls), Cint, (Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}),
+                out, A.m, A.n, A.colptr, A.rowval, A.nzval))
+    return GPUSparseMatrixCSC(Handle(out[]), A.m, A.n)
+end
+"y <- alpha*A*x + beta*y; the cscmv! of sparseblas.jl:14-25 with transa = 'N'."
+function cscmv!(alpha::ComplexF64, A::GPUSparseMatrixCSC, x::Vector{ComplexF64}, beta::ComplexF64, y::Vector{ComplexF64})
+    length(x) == A.n || throw(DimensionMismatch("Matrix with $(A.n) columns multiplied with vector of length $(length(x))"))
+    length(y) == A.m || throw(DimensionMismatch("Vector of length $(A.m) added to vector of length $(length(y))"))
+    check(ccall((:ls_spm_mv, libls), Cint, (Ptr{Cvoid}, ComplexF64, Ptr{ComplexF64}, ComplexF64, Ptr{ComplexF64}, Cint),
+                A.h.ptr, alpha, x, beta, y, LS_MEM_HOST))
+    return y
+end
+*(A::GPUSparseMatrixCSC, x::Vector{ComplexF64}) = cscmv!(1.0 + 0im, A, x, 0.0 + 0im, zeros(ComplexF64, A.m))
+
+struct GPUSparsifyingPreconditioner      # preconditioner.jl:27-58
+    Msp::SparseMatrixCSC{ComplexF64,Int64}
+    As::GPUSparseMatrixCSC
+    MspInv                                 # lu(Msp) (UMFPACK) stays on the host - out of the GPU path's scope
+    solverType::String
+end
+GPUSparsifyingPreconditioner(Msp, As; solverType::String="UMFPACK") =
+    GPUSparsifyingPreconditioner(Msp, GPUSparseMatrixCSC(As), lu(Msp), solverType)
+\(M::GPUSparsifyingPreconditioner, b::Array{ComplexF64,1}) = M.MspInv \ (M.As * b)                     # :132-145
+function ldiv!(M::GPUSparsifyingPreconditioner, b::AbstractArray{ComplexF64,1})                        # :147-166
+    b[:] = M.MspInv \ (M.As * Vector(b))
+end
+
+# ------------------------------------------------------- device-resident GMRES (whole loop on GPU)
+"""
+    gmres_gpu!(x, A, b; Pl=nothing, abstol, reltol, restart, maxiter, log, initially_zero)
+
+Same keywords and history semantics as `IterativeSolvers.gmres!`; the Krylov basis, the modified
+Gram-Schmidt sweeps and the operator applies stay on the device, `Msp^-1` is reached through a
+host callback.
+"""
+function gmres_gpu!(x::Vector{ComplexF64}, A, b::Vector{ComplexF64}; Pl=nothing, abstol=0.0,
+                    reltol=sqrt(eps(Float64)), restart=min(20, length(b)), maxiter=length(b), log=false,
+                    initially_zero=false)
+    N = length(b)
+    kh = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ls_krylov_create, libls), Cint, (Ref{Ptr{Cvoid}}, Int64), kh, N))
+    K = Handle(kh[])
+    hist = zeros(Float64, maxiter); niter = Ref{Int64}(0); conv = Ref{Cint}(0); mv = Ref{Int64}(0)
+    cb = C_NULL; as = C_NULL
+    if Pl !== nothing
+        solve = function (user::Ptr{Cvoid}, v::Ptr{ComplexF64}, n::Int64)::Cint
+            w = unsafe_wrap(Array, v, n)
+            w[:] = Pl.MspInv \ copy(w)
+            return 0
+        end
+        cb = @cfunction($solve, Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64))
+        as = Pl.As.h.ptr
+    end
+    GC.@preserve cb check(ccall((:ls_gmres, libls), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Int64,
+         Float64, Float64, Cint, Ptr{Float64}, Int64, Ref{Int64}, Ref{Cint}, Ref{Int64}, Cint),
+        K.ptr, A.h.ptr, as, cb isa Ptr ? cb : Base.unsafe_convert(Ptr{Cvoid}, cb), C_NULL, b, x, restart, maxiter,
+        reltol, abstol, initially_zero, hist, maxiter, niter, conv, mv, LS_MEM_HOST))
+    return log ? (x, (resnorm=hist[1:niter[]], iters=niter[], isconverged=conv[] != 0, mvps=mv[])) : x
+end
+
+export GPUFastM, GPUFastM3D, GPUSparsifyingPreconditioner, GPUSparseMatrixCSC, fastconvolution, FFTconvolution,
+       gmres_gpu!, cscmv!, set_device
+
+end # module
