@@ -168,8 +168,11 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     {
         LineAddr la{1L << 40, 1, 0, nel * me, 1, 0, nel * me};
         op->phase_begin(2);
+        static int variant = -1;
+        if (variant < 0) { const char* ev = getenv("LS_P3_VARIANT"); variant = ev ? atoi(ev) : 1; }   // 1: spectrum chunks staged by TMA bulk copies (5.96 ms at 256^3), 0: direct loads (7.1 ms)
 #define C3(N) launch_mid<N, true, false>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
-        LS3_DISPATCH(l, C3);
+#define C3T(N) launch_mid<N, true, true>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
+        if (variant == 1) { LS3_DISPATCH(l, C3T); } else { LS3_DISPATCH(l, C3); }
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
