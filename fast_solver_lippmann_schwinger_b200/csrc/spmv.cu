@@ -3,13 +3,25 @@
 // SparseBLAS.cscmv!('N', alpha, "GXXF", A, x, beta, y) (sparseblas.jl:14-25).
 //
 // The matrix arrives exactly as Julia holds it (SparseMatrixCSC{ComplexF64,Int64}: 1-based colptr,
-// rowval, nzval) and is converted once to CSR with 32-bit column indices.  Kernel: a sub-warp of
-// LPR lanes per row (8 lanes for the 9-point 2-D matrix, 32 for the 27-point 3-D one), 128-bit
-// coalesced value loads, warp-shuffle reduction in a fixed order (deterministic).
-// Algorithmic bytes: nnz*20 + 4(N+1) + 32N  (SURVEY.md section 8(d)).
+// rowval, nzval) and is converted once to CSR with 32-bit column indices.  Two device formats:
+//
+//  * stencil classes (fast path).  The sparsifying matrix is built by replicating one coefficient
+//    vector per boundary class at columns row + offsets (createIndices, Functions.jl:7-29;
+//    buildSparseA, SparsifyingMatrix2D.jl:806-884: 9 classes in 2-D, 27 in 3-D).  At create time
+//    rows are grouped by their (relative offsets, values) signature; if that yields few classes,
+//    the device keeps one byte per row plus the tiny class tables, so a multiply moves
+//    ~33 B/row instead of the 216 B/row of CSR.  Detection is exact (bitwise equality of values),
+//    so any matrix without that structure simply takes the CSR path.
+//  * CSR, a sub-warp of LPR lanes per row (8 lanes for ~9 nnz/row, 32 for ~27), 128-bit
+//    coalesced value loads, warp-shuffle reduction in a fixed order.
+// Both sum each row in increasing column order, like SparseArrays' column-scatter loop.
+// Algorithmic bytes (CSR accounting): nnz*20 + 4(N+1) + 32N.
 #include "ls_common.cuh"
 #include "spmv.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
 
 using namespace ls;
 
@@ -48,10 +60,47 @@ k_spmv_csr(const int* __restrict__ rowptr, const int* __restrict__ col, const cd
     }
 }
 
+// one thread per row; class tables (<= SPM_MAX_CLASS_ENTRIES entries) staged in shared memory
+__global__ void __launch_bounds__(256)
+k_spmv_stencil(const unsigned char* __restrict__ cls, const int* __restrict__ cls_ptr, const int* __restrict__ cls_off,
+               const cd* __restrict__ cls_val, int ncls, int nent, const cd* __restrict__ x, cd* y,
+               cd alpha, cd beta, int use_beta, long nrows) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    cd* sval = reinterpret_cast<cd*>(smraw);
+    int* soff = reinterpret_cast<int*>(sval + nent);
+    int* sptr = soff + nent;
+    for (int i = threadIdx.x; i < nent; i += blockDim.x) { sval[i] = cls_val[i]; soff[i] = cls_off[i]; }
+    for (int i = threadIdx.x; i <= ncls; i += blockDim.x) sptr[i] = cls_ptr[i];
+    __syncthreads();
+    for (long row = (long)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (long)gridDim.x * blockDim.x) {
+        const int c = cls[row];
+        const int p0 = sptr[c], p1 = sptr[c + 1];
+        double sr = 0.0, si = 0.0;
+        for (int p = p0; p < p1; ++p) {
+            const cd a = sval[p];
+            const cd xv = __ldg(&x[row + soff[p]]);
+            sr += a.x * xv.x - a.y * xv.y;
+            si += a.x * xv.y + a.y * xv.x;
+        }
+        cd r = make_double2(alpha.x * sr - alpha.y * si, alpha.x * si + alpha.y * sr);
+        if (use_beta) {
+            const cd y0 = y[row];
+            r.x += beta.x * y0.x - beta.y * y0.y;
+            r.y += beta.x * y0.y + beta.y * y0.x;
+        }
+        y[row] = r;
+    }
+}
+
 int SpM::mv_dev(cd alpha, const cd* x, cd beta, cd* y, cudaStream_t s) {
     const int use_beta = (beta.x != 0.0 || beta.y != 0.0) ? 1 : 0;
     const int th = 256;
-    if (lanes_per_row == 8) {
+    if (format == SPM_FORMAT_STENCIL) {
+        const size_t smem = (size_t)nent * (sizeof(cd) + sizeof(int)) + (size_t)(ncls + 1) * sizeof(int);
+        long blocks = std::min<long>((nrows + th - 1) / th, 148L * 32);
+        k_spmv_stencil<<<(unsigned)blocks, th, smem, s>>>(d_cls, d_cls_ptr, d_cls_off, d_cls_val, ncls, nent, x, y,
+                                                          alpha, beta, use_beta, nrows);
+    } else if (lanes_per_row == 8) {
         long blocks = (nrows * 8 + th - 1) / th;
         k_spmv_csr<8><<<(unsigned)blocks, th, 0, s>>>(d_rowptr, d_col, d_val, x, y, alpha, beta, use_beta, nrows);
     } else {
@@ -64,6 +113,65 @@ int SpM::mv_dev(cd alpha, const cd* x, cd beta, cd* y, cudaStream_t s) {
 }
 
 }  // namespace ls
+
+namespace {
+
+constexpr int SPM_MAX_CLASSES = 255;
+constexpr int SPM_MAX_CLASS_ENTRIES = 2048;
+
+// groups rows by (relative offsets, values); returns false when the matrix has no small class structure
+bool detect_stencil_classes(long nrows, const std::vector<int>& rowptr, const std::vector<int>& col,
+                            const std::vector<cd>& val, std::vector<unsigned char>& cls,
+                            std::vector<int>& cls_ptr, std::vector<int>& cls_off, std::vector<cd>& cls_val) {
+    struct Rep { long row; int id; };
+    std::unordered_map<uint64_t, std::vector<Rep>> table;
+    cls.assign((size_t)nrows, 0);
+    cls_ptr.assign(1, 0);
+    cls_off.clear();
+    cls_val.clear();
+    int ncls = 0;
+    auto same = [&](long r0, long r1) {
+        const int a0 = rowptr[r0], a1 = rowptr[r1];
+        const int len = rowptr[r0 + 1] - a0;
+        if (rowptr[r1 + 1] - a1 != len) return false;
+        for (int i = 0; i < len; ++i) {
+            if ((long)col[a0 + i] - r0 != (long)col[a1 + i] - r1) return false;
+            if (memcmp(&val[a0 + i], &val[a1 + i], sizeof(cd)) != 0) return false;
+        }
+        return true;
+    };
+    for (long r = 0; r < nrows; ++r) {
+        uint64_t hsh = 1469598103934665603ULL;
+        auto mix = [&](uint64_t v) { hsh ^= v; hsh *= 1099511628211ULL; };
+        for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) {
+            mix((uint64_t)((long)col[p] - r));
+            uint64_t bits[2];
+            memcpy(bits, &val[p], sizeof(bits));
+            mix(bits[0]);
+            mix(bits[1]);
+        }
+        mix((uint64_t)(rowptr[r + 1] - rowptr[r]));
+        auto& bucket = table[hsh];
+        int id = -1;
+        for (const Rep& rep : bucket)
+            if (same(rep.row, r)) { id = rep.id; break; }
+        if (id < 0) {
+            if (ncls == SPM_MAX_CLASSES) return false;
+            id = ncls++;
+            bucket.push_back(Rep{r, id});
+            for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) {
+                cls_off.push_back((int)((long)col[p] - r));
+                cls_val.push_back(val[p]);
+            }
+            cls_ptr.push_back((int)cls_off.size());
+            if ((int)cls_off.size() > SPM_MAX_CLASS_ENTRIES) return false;
+        }
+        cls[(size_t)r] = (unsigned char)id;
+    }
+    return true;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -104,9 +212,25 @@ int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* c
     const double avg = (double)nnz / (double)nrows;
     A->lanes_per_row = avg <= 12.0 ? 8 : 32;
 #define TRY(x) do { rc = (x); if (rc) { delete A; return rc; } } while (0)
-    TRY(A->dupload((void**)&A->d_rowptr, rowptr.data(), rowptr.size() * sizeof(int)));
-    TRY(A->dupload((void**)&A->d_col, col.data(), std::max<size_t>(col.size(), 1) * sizeof(int)));
-    TRY(A->dupload((void**)&A->d_val, val.data(), std::max<size_t>(val.size(), 1) * sizeof(cd)));
+    const char* force = getenv("LS_SPM_FORCE_CSR");
+    std::vector<unsigned char> cls;
+    std::vector<int> cls_ptr, cls_off;
+    std::vector<cd> cls_val;
+    if (!(force && atoi(force)) && nrows == ncols &&
+        detect_stencil_classes(nrows, rowptr, col, val, cls, cls_ptr, cls_off, cls_val) && !cls_off.empty()) {
+        A->format = SPM_FORMAT_STENCIL;
+        A->ncls = (int)cls_ptr.size() - 1;
+        A->nent = (int)cls_off.size();
+        TRY(A->dupload((void**)&A->d_cls, cls.data(), cls.size()));
+        TRY(A->dupload((void**)&A->d_cls_ptr, cls_ptr.data(), cls_ptr.size() * sizeof(int)));
+        TRY(A->dupload((void**)&A->d_cls_off, cls_off.data(), cls_off.size() * sizeof(int)));
+        TRY(A->dupload((void**)&A->d_cls_val, cls_val.data(), cls_val.size() * sizeof(cd)));
+    } else {
+        A->format = SPM_FORMAT_CSR;
+        TRY(A->dupload((void**)&A->d_rowptr, rowptr.data(), rowptr.size() * sizeof(int)));
+        TRY(A->dupload((void**)&A->d_col, col.data(), std::max<size_t>(col.size(), 1) * sizeof(int)));
+        TRY(A->dupload((void**)&A->d_val, val.data(), std::max<size_t>(val.size(), 1) * sizeof(cd)));
+    }
     TRY(A->dmalloc((void**)&A->d_x, (size_t)ncols * sizeof(cd)));
     TRY(A->dmalloc((void**)&A->d_y, (size_t)nrows * sizeof(cd)));
 #undef TRY
@@ -135,13 +259,15 @@ int ls_spm_mv(ls_handle h, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble bet
     return LS_OK;
 }
 
-int ls_spm_info(ls_handle h, int64_t* nrows, int64_t* ncols, int64_t* nnz) {
+int ls_spm_info(ls_handle h, int64_t* nrows, int64_t* ncols, int64_t* nnz, int* format, int* nclasses) {
     LS_REQUIRE(h, LS_ERR_INVALID, "ls_spm_info: null handle");
     SpM* A = reinterpret_cast<SpM*>(h);
     LS_REQUIRE(A->kind == KIND_SPM, LS_ERR_INVALID, "ls_spm_info: not a sparse-matrix handle");
     if (nrows) *nrows = A->nrows;
     if (ncols) *ncols = A->ncols;
     if (nnz) *nnz = A->nnz;
+    if (format) *format = A->format;
+    if (nclasses) *nclasses = A->format == SPM_FORMAT_STENCIL ? A->ncls : 0;
     return LS_OK;
 }
 

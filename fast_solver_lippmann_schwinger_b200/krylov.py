@@ -49,6 +49,10 @@ class GPUSparseMatrixCSC(_Handle):
         self.shape = (nrows, ncols)
         self.nnz = int(colptr[-1] - 1)
         check(lib().ls_spm_create(C.byref(self._h), nrows, ncols, ptr(colptr), ptr(rowval), ptr(nzval)))
+        fmt, ncl = C.c_int(), C.c_int()
+        check(lib().ls_spm_info(self.handle, None, None, None, C.byref(fmt), C.byref(ncl)))
+        self.format = "stencil" if fmt.value == 1 else "csr"      # device storage chosen at create time
+        self.nclasses = int(ncl.value)
 
     def mv(self, x, y=None, alpha=1.0, beta=0.0):
         """y <- alpha*A*x + beta*y  (cscmv! with transa='N')."""

@@ -109,7 +109,9 @@ int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* c
  * same meaning as SparseBLAS.cscmv!('N', alpha, "GXXF", A, x, beta, y), sparseblas.jl:14-25.
  * x and y must not alias.                                                                  */
 int ls_spm_mv(ls_handle A, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble beta, ls_cdouble* y, int memloc);
-int ls_spm_info(ls_handle A, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+/* device format: 0 = CSR (sub-warp per row), 1 = stencil classes (rows grouped by identical
+ * (relative offsets, values) - the structure buildSparseA produces; exact detection at create) */
+int ls_spm_info(ls_handle A, int64_t* nrows, int64_t* ncols, int64_t* nnz, int* format, int* nclasses);
 
 /* ---- GMRES Arnoldi vector kernels (IterativeSolvers.jl gmres!, un-vendored; call sites ------ *
  * examples/example.jl:85,91).  A Krylov workspace owns the reduction buffers for vectors of

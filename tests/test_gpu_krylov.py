@@ -40,8 +40,21 @@ def test_spmv_matches_csc_loop():
     x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
     A = ls.GPUSparseMatrixCSC(As)
     assert A.nnz == As.nnz == 9 * 62 * 62 + 24 * 62 + 16
+    assert A.format == "stencil" and A.nclasses == 9          # the 9 boundary classes of buildSparseA
     y = A * x
     assert _rel(y, O.csc_matvec(As, x)) < 1e-13
+    # the general CSR kernel on the same matrix (structure detection switched off)
+    import os
+    os.environ["LS_SPM_FORCE_CSR"] = "1"
+    try:
+        Acsr = ls.GPUSparseMatrixCSC(As)
+    finally:
+        del os.environ["LS_SPM_FORCE_CSR"]
+    assert Acsr.format == "csr"
+    assert _rel(Acsr * x, O.csc_matvec(As, x)) < 1e-13
+    # Msp has a position-dependent contrast: no class structure, CSR path
+    assert ls.GPUSparseMatrixCSC(Msp).format == "csr"
+    assert _rel(ls.GPUSparseMatrixCSC(Msp) * x, Msp @ x) < 1e-13
     # Julia-layout arrays + the pure loop statement on a small slice of columns
     cp, rv, nz = O.julia_csc_arrays(As)
     A2 = ls.GPUSparseMatrixCSC((N, N, cp, rv, nz))
