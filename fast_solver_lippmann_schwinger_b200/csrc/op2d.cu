@@ -6,6 +6,7 @@
 //   P3  k_inv_pruned  columns (x): C, b                    -> y
 // Algorithmic HBM bytes per apply: 568*N  (SURVEY.md section 8(d)).
 #include "ls_common.cuh"
+#include "op2d_base.cuh"
 #include "line_kernels.cuh"
 
 using namespace ls;
@@ -13,17 +14,12 @@ using namespace lsk;
 
 namespace {
 
-struct Op2D : HandleBase {
-    long n = 0, m = 0, ne = 0, me = 0;
-    double omega = 0;
-    int quadrule = 0;
+struct Op2D : Op2DBase {
     double* d_nu = nullptr;
     cd* d_G = nullptr;        // [sx][ry][slot_y], scaled by 1/(ne*me)
     cd* d_TABn = nullptr; cd* d_TABm = nullptr;   // engine tables (fft_engine.cuh EngTab)
     cd* d_A = nullptr;        // ne x m
     cd* d_C = nullptr;        // m x ne (line contiguous)
-    cd* d_b = nullptr; cd* d_y = nullptr;   // staging for host-pointer applies
-    int64_t op_size() const override { return n * m; }
     int apply_dev(const cd* b, cd* y, int mode) override;
 };
 
@@ -138,7 +134,6 @@ extern "C" {
 
 int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
                    const double* nu, const ls_cdouble* gfft, double omega, int quadrule, int flags) {
-    (void)flags;
     LS_REQUIRE(out && nu && gfft, LS_ERR_INVALID, "ls_op2d_create: null pointer");
     LS_REQUIRE(n > 0 && m > 0 && ne > 0 && me > 0, LS_ERR_INVALID, "ls_op2d_create: non-positive size");
     LS_REQUIRE(quadrule == LS_QUAD_TRAPEZOIDAL || quadrule == LS_QUAD_GREENGARD_VICO, LS_ERR_INVALID,
@@ -146,13 +141,12 @@ int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
     if (quadrule == LS_QUAD_TRAPEZOIDAL) {
         LS_REQUIRE(ne == 2 * n - 1 && me == 2 * m - 1, LS_ERR_INVALID,
                    "ls_op2d_create: trapezoidal needs ne = 2n-1, me = 2m-1 (FastConvolution.jl:183)");
-        LS_REQUIRE(false, LS_ERR_UNSUPPORTED,
-                   "ls_op2d_create: trapezoidal quadrature (odd, non power-of-two FFT sizes) is not served by the GPU path yet");
+        return create_op2d_generic(out, n, m, ne, me, nu, gfft, omega, quadrule);
     }
     LS_REQUIRE(ne == 4 * n && me == 4 * m, LS_ERR_INVALID,
                "ls_op2d_create: Greengard_Vico needs ne = 4n, me = 4m (FastConvolution.jl:201)");
-    LS_REQUIRE(fft_size_supported(n) && fft_size_supported(m), LS_ERR_UNSUPPORTED,
-               "ls_op2d_create: n=%ld, m=%ld - the GPU path serves powers of two in [64, 4096]", (long)n, (long)m);
+    if (!(fft_size_supported(n) && fft_size_supported(m)) || (flags & LS_FLAG_FORCE_GENERIC))
+        return create_op2d_generic(out, n, m, ne, me, nu, gfft, omega, quadrule);
 
     Op2D* op = new Op2D();
     int rc = op->init_base(KIND_OP2D);
@@ -193,7 +187,7 @@ int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
 
 int ls_op2d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc) {
     LS_REQUIRE(h && b && y, LS_ERR_INVALID, "ls_op2d_apply: null argument");
-    Op2D* op = reinterpret_cast<Op2D*>(h);
+    Op2DBase* op = reinterpret_cast<Op2DBase*>(h);
     LS_REQUIRE(op->kind == KIND_OP2D, LS_ERR_INVALID, "ls_op2d_apply: not a 2-D operator handle");
     LS_REQUIRE(mode == LS_APPLY_FASTCONVOLUTION || mode == LS_APPLY_FFTCONVOLUTION, LS_ERR_INVALID,
                "ls_op2d_apply: unknown mode %d", mode);
@@ -203,11 +197,11 @@ int ls_op2d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int
     LS_CUDA_TRY(cudaSetDevice(op->device));
     const size_t bytes = (size_t)op->n * op->m * sizeof(cd);
     if (memloc == LS_MEM_DEVICE) {
-        return apply_device(op, reinterpret_cast<const cd*>(b), reinterpret_cast<cd*>(y), mode);
+        return op->apply_dev(reinterpret_cast<const cd*>(b), reinterpret_cast<cd*>(y), mode);
     }
     LS_REQUIRE(memloc == LS_MEM_HOST, LS_ERR_INVALID, "ls_op2d_apply: unknown memloc %d", memloc);
     LS_CUDA_TRY(cudaMemcpyAsync(op->d_b, b, bytes, cudaMemcpyHostToDevice, op->stream));
-    int rc = apply_device(op, op->d_b, op->d_y, mode);
+    int rc = op->apply_dev(op->d_b, op->d_y, mode);
     if (rc) return rc;
     LS_CUDA_TRY(cudaMemcpyAsync(y, op->d_y, bytes, cudaMemcpyDeviceToHost, op->stream));
     LS_CUDA_TRY(cudaStreamSynchronize(op->stream));

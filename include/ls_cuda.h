@@ -37,6 +37,9 @@ typedef struct ls_handle_s* ls_handle;
 #define LS_ERR_NCCL        -5
 #define LS_ERR_CALLBACK    -6
 
+/* create flags */
+#define LS_FLAG_FORCE_GENERIC 1   /* take the general-size (Bluestein) path even for power-of-two grids (tests) */
+
 #define LS_MEM_HOST   0
 #define LS_MEM_DEVICE 1
 
@@ -66,8 +69,11 @@ int ls_host_free_pinned(void* hptr);
  * create copies nu (n*m doubles) and GFFT (ne*me complex, column-major, the reference's
  * centred ordering for Greengard_Vico - the fftshift/ifftshift pair of FastConvolution.jl:94,98
  * is folded into a one-time permutation) to the device.  Nothing of the caller's memory is
- * kept.  Served on the GPU fast path: Greengard_Vico with ne = 4n, me = 4m and n, m in
- * {64,...,4096} powers of two.                                                           */
+ * kept.  Fast path: Greengard_Vico with ne = 4n, me = 4m and n, m in {64,...,4096} powers of
+ * two (pruned radix-8/16 transforms).  Every other case the reference accepts - any n, m
+ * (examples/example.jl ships n = 201, ne = 804) and the trapezoidal rule (ne = 2n-1, crop
+ * [n:2n-1], FastConvolution.jl:64-83) - runs on the general path: arbitrary-length line DFTs
+ * by Bluestein's algorithm on the same engine, as long as ne + n - 1 <= 4096.             */
 int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
                    const double* nu, const ls_cdouble* gfft, double omega,
                    int quadrule, int flags);

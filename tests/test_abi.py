@@ -55,9 +55,12 @@ def test_error_paths_without_gpu(built_lib):
     g = np.zeros(16, complex)
     rc = L.ls_op2d_create(C.byref(h), 2, 2, 9, 8, nu.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), 1.0, 1, 0)
     assert rc == -1 and b"ne = 4n" in L.ls_last_error()
-    rc = L.ls_op2d_create(C.byref(h), 3, 3, 5, 5, nu.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), 1.0, 0, 0)
-    assert rc == -2 and b"trapezoidal" in L.ls_last_error()
-    rc = L.ls_op2d_create(C.byref(h), 96, 96, 384, 384, nu.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), 1.0, 1, 0)
+    rc = L.ls_op2d_create(C.byref(h), 3, 3, 6, 5, nu.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), 1.0, 0, 0)
+    assert rc == -1 and b"trapezoidal needs ne = 2n-1" in L.ls_last_error()
+    # valid upstream, too large for the general-size GPU path: refused loudly, before any CUDA call
+    rc = L.ls_op2d_create(C.byref(h), 1000, 1000, 4000, 4000, nu.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), 1.0, 1, 0)
+    assert rc == -2 and b"4096" in L.ls_last_error()
+    rc = L.ls_op2d_create(C.byref(h), 2049, 2049, 4097, 4097, nu.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), 1.0, 0, 0)
     assert rc == -2
     rc = L.ls_op2d_apply(None, None, None, 0, 0)
     assert rc == -1

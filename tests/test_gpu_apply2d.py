@@ -85,9 +85,8 @@ def test_linearity_and_device_buffers():
 
 def test_unsupported_and_invalid_inputs():
     import fast_solver_lippmann_schwinger_b200 as ls
-    g = np.zeros((41, 41), dtype=np.complex128)
-    with pytest.raises(ls.LSUnsupported):
-        ls.FastM(g, np.zeros(21 * 21), 41, 41, 21, 21, 20.0)           # trapezoidal: not on the GPU path yet
+    with pytest.raises(ls.LSUnsupported):                               # padded line too long for the general path
+        ls.FastM(np.zeros((4000, 8), complex), np.zeros(1000 * 2), 4000, 8, 1000, 2, 1.0, quadRule="Greengard_Vico")
     M = ls.FastM(np.zeros((256, 256), complex), np.zeros(64 * 64), 256, 256, 64, 64, 1.0, quadRule="Greengard_Vico")
     with pytest.raises(ValueError):
         M * np.zeros(5, complex)                                       # DimensionMismatch
