@@ -200,10 +200,14 @@ __device__ __forceinline__ void st_stage(const cd* v, int t, cd* sm, const Lay& 
 template <int N, int I, class Lay>
 __device__ __forceinline__ void ld_stage(cd* v, int t, const cd* sm, const Lay& lay) {
     typedef Stage<N, I> St;
+    // issue order = consumption order of the butterfly's first layer (dft4 over a, a+R/4, a+R/2, a+3R/4)
 #pragma unroll
     for (int u = 0; u < St::NB; ++u)
 #pragma unroll
-        for (int a = 0; a < St::R; ++a) v[u * St::R + a] = sm[lay.phys(St::addr(t, u, a))];
+        for (int i = 0; i < St::R; ++i) {
+            const int a = (St::R >= 4) ? (i % 4) * (St::R / 4) + i / 4 : i;
+            v[u * St::R + a] = sm[lay.phys(St::addr(t, u, a))];
+        }
 }
 
 // ------------------------------------------------------------------------------------
@@ -336,19 +340,26 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
 // Forward FFT of sub-transform r of one line.  In: v[a] = x[a*T + t].  Out: v[e] = X_r[freq(t + T*e)],
 // X_r = FFT_N(x[j] w_{4N}^{r j}).  sm/lay = this line's exchange buffer (N points).
-template <int N, class Lay>
-__device__ __forceinline__ void fft_fwd(cd* v, int t, int r, cd* sm, const Lay& lay, const TwState<N>& tw) {
+// `pre_last` runs on every thread just before the butterflies of the last stage (the place to issue
+// global loads whose latency should hide behind them).
+template <int N, class Lay, class Hook = NoHook>
+__device__ __forceinline__ void fft_fwd(cd* v, int t, int r, cd* sm, const Lay& lay, const TwState<N>& tw,
+                                        Hook pre_last = Hook()) {
     typedef Cfg<N> C;
     fwd_stage0<N>(v, r, tw);
     st_stage<N, 0>(v, t, sm, lay);
     __syncthreads();
     ld_stage<N, 1>(v, t, sm, lay);
-    fwd_stage<N, 1>(v, t, tw);
     if constexpr (C::S == 3) {
+        fwd_stage<N, 1>(v, t, tw);
         st_stage<N, 1>(v, t, sm, lay);
         __syncthreads();
         ld_stage<N, 2>(v, t, sm, lay);
+        pre_last();
         fwd_stage<N, 2>(v, t, tw);
+    } else {
+        pre_last();
+        fwd_stage<N, 1>(v, t, tw);
     }
 }
 
@@ -398,6 +409,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace lsfft

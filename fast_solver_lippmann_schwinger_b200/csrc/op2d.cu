@@ -56,7 +56,9 @@ template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
     return LS_OK;
 }
 template <int N, bool GSM, int MINB> int launch_mid_v(Op2D* op) {
-    constexpr int smem = GSM ? Smem<N, false>::mid_bytes : Smem<N, false>::mid_bytes_direct;
+    static int extra = -1;      // diagnostic: LS_P2_EXTRA_SMEM pads the request to lower the CTAs/SM
+    if (extra < 0) { const char* e = getenv("LS_P2_EXTRA_SMEM"); extra = e ? atoi(e) : 0; }
+    const int smem = (GSM ? Smem<N, false>::mid_bytes : Smem<N, false>::mid_bytes_direct) + extra;
     static bool attr = false;
     if (!attr) {
         LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false, GSM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
