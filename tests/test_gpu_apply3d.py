@@ -56,3 +56,52 @@ def test_3d_device_buffers_inplace_and_errors():
         ls.FastM3D(None, np.zeros(64 * 128 * 64), 256, 512, 256, 64, 128, 64, 1.0, L=1.0, Lp=4.0)
     with pytest.raises(ls.LSUnsupported):
         ls.FastM3D(None, np.zeros(48 ** 3), 192, 192, 192, 48, 48, 48, 48.0, L=1.8, Lp=4.0)   # example3D.jl size: not a power of two
+
+
+def test_long_z_lines_512():
+    """k_mid_fused<512, mode B> (the 512^3 / 8-GPU configuration's z pass) against the oracle."""
+    from oracle import ls_oracle as O
+    import fast_solver_lippmann_schwinger_b200 as ls
+    n, l = 64, 512
+    h = 1.0 / l
+    x = -0.5 * n / l + h * np.arange(n)
+    z = -0.5 + h * np.arange(l)
+    k = 2 * np.pi / (10 * h)
+    nu = lambda X, Y, Z: 0.3 * np.exp(-40 * (16 * X ** 2 + 16 * Y ** 2 + Z ** 2))
+    Mo = O.buildFastConvolution3D(x, x, z, h, k, nu)
+    Mg = ls.FastM3D(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.le, n, n, l, k)
+    rng = np.random.default_rng(99)
+    b = rng.standard_normal(n * n * l) + 1j * rng.standard_normal(n * n * l)
+    assert _rel(Mg * b, Mo * b) <= TOL
+
+
+def test_y_lines_512_properties():
+    """k_fwd_pruned / k_inv_pruned<512, mode B> on a 512 x 512 x 64 grid: too large for the oracle,
+    checked by reciprocity and linearity."""
+    import fast_solver_lippmann_schwinger_b200 as ls
+    n, l = 512, 64
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    x = -0.5 + h * np.arange(n)
+    z = -0.5 * l / n + h * np.arange(l)
+    g = np.exp(-40 * x ** 2)
+    gz = np.exp(-40 * (8 * z) ** 2)
+    nu = np.ascontiguousarray((0.3 * g[:, None, None] * g[None, :, None] * gz[None, None, :]).reshape(-1, order="F"))
+    M = ls.FastM3D(None, nu, 4 * n, 4 * n, 4 * l, n, n, l, k, L=1.8 * n * h, Lp=4.0 * n * h)
+    N = n * n * l
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    c = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    assert _rel(M * (b + 2j * c), M * b + 2j * (M * c)) <= 1e-13
+    ia, ib = (250, 260, 30), (262, 247, 35)
+    a_idx = ia[0] + n * ia[1] + n * n * ia[2]
+    b_idx = ib[0] + n * ib[1] + n * n * ib[2]
+    ea = np.zeros(N, complex); ea[a_idx] = 1.0
+    eb = np.zeros(N, complex); eb[b_idx] = 1.0
+    ra = (M * ea)[b_idx] / nu[a_idx]
+    rb = (M * eb)[a_idx] / nu[b_idx]
+    assert abs(ra - rb) <= 1e-11 * abs(ra)
+    # (no Green's-function check here: upstream uses the x extent for every wave-number axis
+    #  (FastConvolution3D.jl:72-79), so for l != n the kernel is not the free-space one - a reference
+    #  quirk both the oracle and the device generator reproduce; the cubic case is checked in
+    #  tests/test_gpu_fullsize.py)
