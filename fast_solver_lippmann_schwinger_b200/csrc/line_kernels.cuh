@@ -95,7 +95,8 @@ template <int N, bool MODE_B> struct Smem {
 // in  : line L point j at in[L*in_ls + j*in_es], optionally scaled by the real nu (same addressing)
 // out : line L slot  s at out[L*out_ls + s*out_es], s = r*N + slot
 template <int N, bool MODE_B>
-__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
+__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS,
+                                  ((MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS) <= 128) ? 3 : 1)   // 128-thread CTAs: 168 regs, 3 CTAs/SM
 k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __restrict__ out,
              const cd* __restrict__ TAB, const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
@@ -245,8 +246,10 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
 // ---- inverse, pruned: 4N slots -> N outputs, optional identity-plus-contrast combine --
 // in  : line L slot s at in[L*in_ls + s*in_es]
 // out : line L point j at out[L*out_ls + j*out_es];  if bsrc: out = bsrc + scale*result
-template <int N, bool MODE_B>
-__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS)
+// PF: contiguous lines only - pull the next slot block (and the b values) into L2 one block ahead
+template <int N, bool MODE_B, bool PF = false>
+__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS,
+                                  ((MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS) <= 128) ? 3 : 1)
 k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __restrict__ TAB, double scale,
              const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
@@ -271,7 +274,8 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __res
         // pull the next block (or, at the end, the b values of the combine) into L2 while this one is transformed
         // (contiguous lines only: measured on B200, prefetching scattered 16-byte pieces costs more L2
         //  requests than the latency it hides - 2-D P3 0.177 -> 0.223 ms, 3-D P5 0.54 -> 0.44 ms)
-        if (r < 3) {
+        if (!PF) {
+        } else if (r < 3) {
             if (!MODE_B && la.in_es == 1 && (t & 7) == 0) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) prefetch_l2(&p[slot_off(la, (long)((r + 1) * N + t + T * e), 1)]);
@@ -328,18 +332,18 @@ inline cudaError_t launch_mid(cudaStream_t s, long nlines, const cd* in, cd* out
     return cudaPeekAtLastError();
 }
 
-template <int N, bool B>
+template <int N, bool B, bool PF = false>
 inline cudaError_t launch_inv(cudaStream_t s, long nlines, const cd* in, const cd* bsrc, cd* out, const cd* TAB,
                               double scale, const LineAddr& la) {
     constexpr int smem = Smem<N, B>::fwd_bytes;
     constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_inv_pruned<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(k_inv_pruned<N, B, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    k_inv_pruned<N, B><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, bsrc, out, TAB, scale, la, 0);
+    k_inv_pruned<N, B, PF><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, bsrc, out, TAB, scale, la, 0);
     return cudaPeekAtLastError();
 }
 

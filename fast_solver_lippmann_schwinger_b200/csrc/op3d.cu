@@ -196,7 +196,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
         LineAddr la{1L << 40, nel, 0, 1, n, 0, 1};
         la.split_shift = shift; la.split_stride = blk;
         op->phase_begin(4);
-#define C5(N) launch_inv<N, false>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
+#define C5(N) launch_inv<N, false, true>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
         LS3_DISPATCH(n, C5);
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
