@@ -168,3 +168,37 @@ def test_gmres_restart_and_device_vectors():
     assert hg.iters == len(hist_o) == 23 and hg.mvps == mv_o
     assert np.max(np.abs(hg["resnorm"] - hist_o) / hist_o) < 1e-8
     assert _rel(dx.to_host(), xo) < 1e-8
+
+
+def test_plasma_contrast_preconditioned_solve():
+    """Config 3 (tests/plasma_example.jl) at reduced size: discontinuous plasma contrast, Greengard_Vico
+    operator, sparsifying preconditioner, rhs = -(A u_inc - u_inc) (plasma_example.jl:160-161)."""
+    from oracle import ls_oracle as O
+    from oracle.gmres_is import gmres as gmres_oracle
+    import fast_solver_lippmann_schwinger_b200 as ls
+    n = 128
+    h = 1.0 / n
+    x = -0.5 + h * np.arange(n)
+    k = 1.0 / h
+    Mo = O.buildFastConvolution(x, x, h, k, O.nu_plasma_2d, quadRule="Greengard_Vico")
+    assert np.unique(Mo.nu).size > 100 and (Mo.nu == 0).sum() > 100          # genuinely discontinuous profile
+    X, Y = O.grid2d(x, x)
+    D0 = O.referenceValsTrapRule()[1][0]
+    cache = O.entriesSparseA(k, X, Y, D0, n, n, strict=False)
+    As = O.buildSparseA(k, X, Y, D0, n, n, strict=False, _cache=cache)
+    AG = O.buildSparseAG(k, X, Y, D0, n, n, strict=False, _cache=cache)
+    Msp = (As + k ** 2 * (AG @ sp.diags(Mo.nu))).tocsc()
+    Mg = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, n, n, k, quadRule="Greengard_Vico")
+    u_inc = np.exp(1j * k * X)
+    rhs_o = -(O.fastconvolution(Mo, u_inc) - u_inc)
+    rhs_g = -(Mg * u_inc - u_inc)
+    assert _rel(rhs_g, rhs_o) < 1e-12
+    Po, Pg = O.SparsifyingPreconditioner(Msp, As), ls.SparsifyingPreconditioner(Msp, As)
+    xo = np.zeros(n * n, complex)
+    xo, hist_o, conv_o, _ = gmres_oracle(xo, lambda v: O.fastconvolution(Mo, v), rhs_o, Pl_ldiv=Po.solve, maxiter=80)
+    xg = np.zeros(n * n, complex)
+    xg, hg = ls.gmres_(xg, Mg, rhs_o, Pl=Pg, log=True, maxiter=80)
+    assert hg.iters == len(hist_o) and hg.isconverged == conv_o
+    m = min(50, len(hist_o))
+    assert np.max(np.abs(hg["resnorm"][:m] - hist_o[:m]) / hist_o[:m]) < 1e-8
+    assert _rel(xg, xo) < 1e-7
