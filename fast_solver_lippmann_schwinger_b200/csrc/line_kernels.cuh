@@ -144,12 +144,15 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
 //       -> per (unit, r) one contiguous chunk, fetched by TMA bulk copy into shared memory
 //          while the previous block's inverse transform runs.
 // out : line L point j at out[L*out_ls + j*out_es]  (may alias in when strides agree)
-template <int N, bool MODE_B, bool GSM = true, int MINB = 1>
+// ASM: how many of the E per-thread accumulators live in (thread-private) shared memory instead of
+//      registers - the register diet that lets a third CTA fit on the SM.
+template <int N, bool MODE_B, bool GSM = true, int MINB = 1, int ASM = 0>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MINB)
 k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB,
             const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
     constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
+    constexpr int AR = E - ASM, TH = MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
     constexpr int UNIT = MODE_B ? 8 * N : N;          // points per spectrum chunk
     constexpr int UPC = LPC * N / UNIT;               // chunks per CTA and r
     extern __shared__ __align__(128) cd sm[];
@@ -157,7 +160,8 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     cd* ex = sm + sm_group_off(mp);
     cd* xs = sm + LPC * N + sm_group_off(mp);   // thread-private copy of the input line
     cd* gb = sm + 2 * LPC * N;                  // spectrum chunk(s) of the current r (GSM only)
-    cd* tw1 = sm + (GSM ? 3 : 2) * LPC * N;
+    cd* accs = sm + (GSM ? 3 : 2) * LPC * N + threadIdx.x;   // accumulator tail, element k at accs[k*TH]
+    cd* tw1 = sm + (GSM ? 3 : 2) * LPC * N + ASM * TH;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(tw1 + Smem<N, MODE_B>::TW1N);
     const long Lcta = line0 + (long)blockIdx.x * LPC;
     const long L = Lcta + mp.line;
@@ -196,7 +200,7 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     };
     prefetch_g(0);
     __syncthreads();   // tw1 + mbarrier init visible
-    cd acc[E];
+    cd acc[AR];
     const int goff = MODE_B ? 0 : mp.line * N;     // mode B: lay.phys already interleaves the 8 lines
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
@@ -204,7 +208,15 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
 #pragma unroll
         for (int a = 0; a < E; ++a) v[a] = xs[mp.lay.phys(a * T + t)];
         prefetch_g(r + 1);
-        if (!GSM) {
+        if (!GSM && MINB >= 3) {
+            // three CTAs per SM: registers are the scarce resource, the other CTAs hide the load latency
+            fft_fwd<N>(v, t, r, ex, mp.lay, tw);
+            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * 4 + r) * UNIT + mp.lay_lam()
+                                 : gsrc + ((long)mp.line * 4 + r) * UNIT;
+            constexpr int gs = MODE_B ? 8 : 1;
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], __ldg(&g[(t + T * e) * gs]));
+        } else if (!GSM) {
             // spectrum values are requested before the last butterfly stage and consumed after it
             cd gv[E];
             fft_fwd<N>(v, t, r, ex, mp.lay, tw, [&]() {
@@ -236,11 +248,26 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
                 issue_g(r + 1);
             }
         });
-        demod_accumulate<N>(acc, v, r);
+        if (ASM == 0) {
+            demod_accumulate<N>(acc, v, r);
+        } else if (r == 0) {
+#pragma unroll
+            for (int a = 0; a < AR; ++a) acc[a] = v[a];
+#pragma unroll
+            for (int a = AR; a < E; ++a) accs[(a - AR) * TH] = v[a];
+        } else {
+            acc[0] = cadd(acc[0], v[0]);
+#pragma unroll
+            for (int a = 1; a < AR; ++a) acc[a] = cfmac(v[a], c64(r * a * (16 / E)), acc[a]);
+#pragma unroll
+            for (int a = AR; a < E; ++a) accs[(a - AR) * TH] = cfmac(v[a], c64(r * a * (16 / E)), accs[(a - AR) * TH]);
+        }
     }
     cd* o = out + line_out(la, L) + (long)t * la.out_es;
 #pragma unroll
-    for (int a = 0; a < E; ++a) o[(long)(a * T) * la.out_es] = acc[a];
+    for (int a = 0; a < AR; ++a) o[(long)(a * T) * la.out_es] = acc[a];
+#pragma unroll
+    for (int a = AR; a < E; ++a) o[(long)(a * T) * la.out_es] = accs[(a - AR) * TH];
 }
 
 // ---- inverse, pruned: 4N slots -> N outputs, optional identity-plus-contrast combine --

@@ -55,19 +55,20 @@ template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
     op->launches++;
     return LS_OK;
 }
-template <int N, bool GSM, int MINB> int launch_mid_v(Op2D* op) {
+template <int N, bool GSM, int MINB, int ASM = 0> int launch_mid_v(Op2D* op) {
     static int extra = -1;      // diagnostic: LS_P2_EXTRA_SMEM pads the request to lower the CTAs/SM
     if (extra < 0) { const char* e = getenv("LS_P2_EXTRA_SMEM"); extra = e ? atoi(e) : 0; }
-    const int smem = (GSM ? Smem<N, false>::mid_bytes : Smem<N, false>::mid_bytes_direct) + extra;
+    const int smem = (GSM ? Smem<N, false>::mid_bytes : Smem<N, false>::mid_bytes_direct) + extra
+                     + ASM * GeoA<N>::THREADS * (int)sizeof(cd);
     static bool attr = false;
     if (!attr) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false, GSM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false, GSM, MINB, ASM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     dim3 grid((unsigned)(op->ne / GeoA<N>::LPC));
     // line = x slot sx; point j at A[sx + ne*j]; output line contiguous C[j + m*sx]
     op->phase_begin(1);
-    k_mid_fused<N, false, GSM, MINB><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
+    k_mid_fused<N, false, GSM, MINB, ASM><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
         op->d_A, op->d_C, op->d_G, op->d_TABm, LineAddr{1L << 40, 1, 0, op->ne, op->m, 0, 1}, 0);
     op->phase_end();
     op->launches++;
@@ -79,6 +80,8 @@ template <int N> int launch_mid(Op2D* op) {
     // registers (0.706 ms), 0 = spectrum staged in shared memory by TMA bulk copies (0.761 ms)
     if (variant < 0) { const char* e = getenv("LS_P2_VARIANT"); variant = e ? atoi(e) : 1; }
     if (variant == 0) return launch_mid_v<N, true, 1>(op);
+    if (variant == 2) return launch_mid_v<N, false, 3, 4>(op);
+    if (variant == 3) return launch_mid_v<N, false, 3, 2>(op);
     return launch_mid_v<N, false, 1>(op);
 }
 template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
