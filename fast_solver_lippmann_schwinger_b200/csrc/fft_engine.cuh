@@ -389,6 +389,61 @@ __device__ __forceinline__ void fft_inv(cd* v, int t, int r, cd* sm, const Lay& 
     inv_stage0<N>(v, r, tw);
 }
 
+// ---- two sub-transforms in flight per thread --------------------------------------------------
+// The four sub-transforms r = 0..3 of a padded line are independent.  Running two of them through the
+// stages together lets one transform's shared-memory exchange (stores, barrier, loads in flight)
+// overlap the other's FP64 butterflies inside the same warp - the FP64 pipe and the shared-memory
+// pipe are both ~50 % loaded in the fused middle pass and otherwise take turns.
+template <int N, class Lay>
+__device__ __forceinline__ void fft_fwd_dual(cd* vA, cd* vB, int t, int rA, int rB, cd* sm, const Lay& layA, const Lay& layB,
+                                             const TwState<N>& tw) {
+    typedef Cfg<N> C;
+    fwd_stage0<N>(vA, rA, tw);
+    st_stage<N, 0>(vA, t, sm, layA);
+    fwd_stage0<N>(vB, rB, tw);
+    st_stage<N, 0>(vB, t, sm, layB);
+    __syncthreads();
+    ld_stage<N, 1>(vA, t, sm, layA);
+    ld_stage<N, 1>(vB, t, sm, layB);
+    if constexpr (C::S == 3) {
+        fwd_stage<N, 1>(vA, t, tw);
+        st_stage<N, 1>(vA, t, sm, layA);
+        fwd_stage<N, 1>(vB, t, tw);
+        st_stage<N, 1>(vB, t, sm, layB);
+        __syncthreads();
+        ld_stage<N, 2>(vA, t, sm, layA);
+        ld_stage<N, 2>(vB, t, sm, layB);
+        fwd_stage<N, 2>(vA, t, tw);
+        fwd_stage<N, 2>(vB, t, tw);
+    } else {
+        fwd_stage<N, 1>(vA, t, tw);
+        fwd_stage<N, 1>(vB, t, tw);
+    }
+}
+template <int N, class Lay>
+__device__ __forceinline__ void fft_inv_dual(cd* vA, cd* vB, int t, int rA, int rB, cd* sm, const Lay& layA, const Lay& layB,
+                                             const TwState<N>& tw) {
+    typedef Cfg<N> C;
+    if constexpr (C::S == 3) {
+        inv_stage<N, 2>(vA, t, tw);
+        st_stage<N, 2>(vA, t, sm, layA);
+        inv_stage<N, 2>(vB, t, tw);
+        st_stage<N, 2>(vB, t, sm, layB);
+        __syncthreads();
+        ld_stage<N, 1>(vA, t, sm, layA);
+        ld_stage<N, 1>(vB, t, sm, layB);
+    }
+    inv_stage<N, 1>(vA, t, tw);
+    st_stage<N, 1>(vA, t, sm, layA);
+    inv_stage<N, 1>(vB, t, tw);
+    st_stage<N, 1>(vB, t, sm, layB);
+    __syncthreads();
+    ld_stage<N, 0>(vA, t, sm, layA);
+    ld_stage<N, 0>(vB, t, sm, layB);
+    inv_stage0<N>(vA, rA, tw);
+    inv_stage0<N>(vB, rB, tw);
+}
+
 // ---- TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX) -------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {

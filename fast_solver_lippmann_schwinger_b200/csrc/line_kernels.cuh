@@ -270,6 +270,72 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     for (int a = AR; a < E; ++a) o[(long)(a * T) * la.out_es] = accs[(a - AR) * TH];
 }
 
+// ---- middle, fused, two sub-transforms in flight (mode A, spectrum straight from HBM) ----------------
+// Same arithmetic as k_mid_fused; r = 0,1 then r = 2,3 run pairwise through the stages (fft_*_dual).
+// smem: [exchange A: LPC*N][x copy: LPC*N][exchange B: LPC*N][accumulator tail: ASM*TH][tw1]
+template <int N, int ASM>
+__global__ void __launch_bounds__(GeoA<N>::THREADS, 2)
+k_mid_fused_dual(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB,
+                 const LineAddr la, long line0) {
+    typedef Map<N, false> M;
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC, TH = GeoA<N>::THREADS, AR = E - ASM;
+    extern __shared__ __align__(128) cd sm[];
+    M mp;
+    cd* xs = sm + LPC * N;
+    cd* accs = sm + 3 * LPC * N + threadIdx.x;
+    cd* tw1 = sm + 3 * LPC * N + ASM * TH;
+    const long L = line0 + (long)blockIdx.x * LPC + mp.line;
+    const int t = mp.t;
+    LayA<N> layA = mp.lay, layB = mp.lay;
+    layB.base += 2 * LPC * N;
+    load_tw1<N>(tw1, TAB);
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    {
+        const cd* p = in + line_in(la, L) + (long)t * la.in_es;
+#pragma unroll
+        for (int a = 0; a < E; ++a) xs[mp.lay.phys(a * T + t)] = p[(long)(a * T) * la.in_es];
+    }
+    __syncthreads();
+    cd acc[AR > 0 ? AR : 1];
+    const cd* g = G + (L * 4) * (long)N + t;
+#pragma unroll 1
+    for (int rr = 0; rr < 4; rr += 2) {
+        cd vA[E], vB[E];
+#pragma unroll
+        for (int a = 0; a < E; ++a) { vA[a] = xs[mp.lay.phys(a * T + t)]; vB[a] = vA[a]; }
+        fft_fwd_dual<N>(vA, vB, t, rr, rr + 1, sm, layA, layB, tw);
+        const cd* gA = g + (long)rr * N;
+#pragma unroll
+        for (int e = 0; e < E; ++e) vA[e] = cmul(vA[e], __ldg(&gA[T * e]));
+#pragma unroll
+        for (int e = 0; e < E; ++e) vB[e] = cmul(vB[e], __ldg(&gA[N + T * e]));
+        fft_inv_dual<N>(vA, vB, t, rr, rr + 1, sm, layA, layB, tw);
+        // demodulate + accumulate: rr == 0 initialises with r = 0 (no constants), then r = 1; later r = 2, 3
+        if (rr == 0) {
+#pragma unroll
+            for (int a = 0; a < AR; ++a) acc[a] = (a == 0) ? cadd(vA[0], vB[0]) : cfmac(vB[a], c64(a * (16 / E)), vA[a]);
+#pragma unroll
+            for (int a = AR; a < E; ++a) accs[(a - AR) * TH] = cfmac(vB[a], c64(a * (16 / E)), vA[a]);
+        } else {
+#pragma unroll
+            for (int a = 0; a < AR; ++a) {
+                cd z = (a == 0) ? cadd(acc[0], vA[0]) : cfmac(vA[a], c64(2 * a * (16 / E)), acc[a]);
+                acc[a] = (a == 0) ? cadd(z, vB[0]) : cfmac(vB[a], c64(3 * a * (16 / E)), z);
+            }
+#pragma unroll
+            for (int a = AR; a < E; ++a) {
+                cd z = cfmac(vA[a], c64(2 * a * (16 / E)), accs[(a - AR) * TH]);
+                accs[(a - AR) * TH] = cfmac(vB[a], c64(3 * a * (16 / E)), z);
+            }
+        }
+    }
+    cd* o = out + line_out(la, L) + (long)t * la.out_es;
+#pragma unroll
+    for (int a = 0; a < AR; ++a) o[(long)(a * T) * la.out_es] = acc[a];
+#pragma unroll
+    for (int a = AR; a < E; ++a) o[(long)(a * T) * la.out_es] = accs[(a - AR) * TH];
+}
+
 // ---- inverse, pruned: 4N slots -> N outputs, optional identity-plus-contrast combine --
 // in  : line L slot s at in[L*in_ls + s*in_es]
 // out : line L point j at out[L*out_ls + j*out_es];  if bsrc: out = bsrc + scale*result

@@ -74,12 +74,30 @@ template <int N, bool GSM, int MINB, int ASM = 0> int launch_mid_v(Op2D* op) {
     op->launches++;
     return LS_OK;
 }
+template <int N, int ASM> int launch_mid_dual(Op2D* op) {
+    const int smem = (3 * GeoA<N>::LPC * N + EngTab<N>::TW1N + ASM * GeoA<N>::THREADS) * (int)sizeof(cd);
+    static bool attr = false;
+    if (!attr) {
+        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused_dual<N, ASM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid((unsigned)(op->ne / GeoA<N>::LPC));
+    op->phase_begin(1);
+    k_mid_fused_dual<N, ASM><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
+        op->d_A, op->d_C, op->d_G, op->d_TABm, LineAddr{1L << 40, 1, 0, op->ne, op->m, 0, 1}, 0);
+    op->phase_end();
+    op->launches++;
+    return LS_OK;
+}
 template <int N> int launch_mid(Op2D* op) {
     static int variant = -1;
     // variants measured on B200 at 2048^2 (profiles/r1_b_notes.md): 1 = spectrum straight from HBM into
     // registers (0.706 ms), 0 = spectrum staged in shared memory by TMA bulk copies (0.761 ms)
     if (variant < 0) { const char* e = getenv("LS_P2_VARIANT"); variant = e ? atoi(e) : 1; }
     if (variant == 0) return launch_mid_v<N, true, 1>(op);
+    // experiment kept for the record (profiles/r1_b_notes.md): two sub-transforms in flight per thread;
+    // correct, but 255 registers + 590 B of spills make it slower (0.92 ms) - instantiated for 2048 only
+    if constexpr (N == 2048) { if (variant == 5) return launch_mid_dual<N, 4>(op); }
     if (variant == 2) return launch_mid_v<N, false, 3, 4>(op);
     if (variant == 3) return launch_mid_v<N, false, 3, 2>(op);
     return launch_mid_v<N, false, 1>(op);
