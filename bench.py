@@ -218,7 +218,10 @@ def bench_3d(args, ls, lsd, rank, world, local_rank, dist, peak, peak_src):
         "phase_ms": {"P1_x_fwd": per[0], "P2_y_fwd": per[1], "P3_z_fused": per[2], "P4_y_inv": per[3], "P5_x_inv": per[4],
                      "a2a_fwd": per[5], "a2a_back": per[6]},
         "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P3: fused z-line FFT, spectrum multiply, inverse)", "achieved": alg_p3 / (p3 * 1e-3) / 1e9,
-                     "peak": peak, "unit": "GB/s", "frac": alg_p3 / (p3 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "peak": peak, "unit": "GB/s", "frac": alg_p3 / (p3 * 1e-3) / 1e9 / peak,
+                     "traffic": (21.4755e9 + 4.2829e9) * (N / 256.0 ** 3) / world if n == 256 else None,
+                     "traffic_source": "ncu --set full r1_e at 256^3 on one GPU: dram read 21.48 GB + write 4.28 GB (profiles/r1_e_notes.md)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_p3, "launch_ms": p3},
         "apply_roofline": {"algorithmic_bytes_per_apply_per_gpu": 2360.0 * N / world,
                            "frac": 2360.0 * N / world / (ms_step * 1e-3) / 1e9 / peak},
@@ -255,6 +258,51 @@ def bench_gmres(args, ls, M, n, k, h, peak):
             "mv_products": hist.mvps, "ms_per_iter": 1e3 * dt / it, "final_rel_residual": float(hist["resnorm"][-1] / hist["resnorm"][0]) if hist.iters else None,
             "preconditioner": "Identity (the Msp direct solve is host-side and out of scope, SURVEY.md H1)",
             "algorithmic_bytes_per_iter": alg_iter, "hbm_frac": alg_iter / (dt / it) / 1e9 / peak}
+
+
+def bench_krylov_kernels(ls, n, peak):
+    """Sparsifying-matrix SpMV and one fused modified-Gram-Schmidt sweep at the 2-D workload size."""
+    import scipy.sparse as sp
+    N = n * n
+    rng = np.random.default_rng(7)
+    idx = np.arange(N).reshape(n, n, order="F")
+    rows, cols, vals = [], [], []
+    st = rng.standard_normal(9) + 1j * rng.standard_normal(9)
+    for q, (di, dj) in enumerate((a, c) for a in (-1, 0, 1) for c in (-1, 0, 1)):
+        src = idx[max(0, -di):n - max(0, di), max(0, -dj):n - max(0, dj)].ravel()
+        dst = idx[max(0, di):n - max(0, -di), max(0, dj):n - max(0, -dj)].ravel()
+        rows.append(src); cols.append(dst); vals.append(np.full(src.size, st[q]))
+    rows = np.concatenate(rows); cols = np.concatenate(cols)
+    x = ls.DeviceBuffer.from_host(rng.standard_normal(N) + 1j * rng.standard_normal(N))
+    y = ls.DeviceBuffer(16 * N)
+    out = {}
+    # (a) translation-invariant 9-point coefficients (what buildSparseA produces); (b) the same pattern with
+    #     position-dependent values, which has no class structure and takes the CSR kernel
+    for name, v in (("stencil", np.concatenate(vals)), ("csr", rng.standard_normal(rows.size) + 1j * rng.standard_normal(rows.size))):
+        A = sp.csc_matrix((v, (rows, cols)), shape=(N, N))
+        G = ls.GPUSparseMatrixCSC(A)
+        for _ in range(3):
+            G.mv(x, y)
+        G.sync(); G.timer_start()
+        for _ in range(20):
+            G.mv(x, y)
+        ms = G.timer_stop() / 20
+        alg = A.nnz * 20 + 4 * (N + 1) + 32 * N
+        out["spmv_" + name] = {"format": G.format, "nnz": int(A.nnz), "ms": ms, "csr_accounting_bytes": alg,
+                               "GBs": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+        G.destroy()
+    ws = ls.KrylovWorkspace(N)
+    for kk in (10, 20):
+        V = ls.DeviceBuffer(16 * N * (kk + 1))
+        ws.mgs_step(V, N, kk, y)
+        ws.timer_start()
+        for _ in range(10):
+            ws.mgs_step(V, N, kk, y)
+        ms = ws.timer_stop() / 10
+        alg = (64 * kk + 48 + 32) * N
+        out["mgs_k%d" % kk] = {"ms": ms, "algorithmic_bytes": alg, "GBs": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+        V.free()
+    return out
 
 
 def main():
@@ -356,6 +404,7 @@ def main():
     if not args.no_extras:
         if rank == 0 and world == 1:
             extras["gmres"] = bench_gmres(args, ls, M, n, k, h, peak)
+            extras["krylov_kernels"] = bench_krylov_kernels(ls, n, peak)
         barrier()
         M.destroy()
         del db, dy
@@ -378,7 +427,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: 4x forward FFT, spectrum multiply, inverse FFT per padded row)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 1.342e9 + 0.256e9, "traffic_source": "ncu --set full r1_b: dram read 1.342 GB + write 0.256 GB per launch (profiles/r1_b_k_mid_fused_2048.txt)",
+                         "traffic": 1.3422e9 + 0.2545e9, "traffic_source": "ncu --set full r1_d: dram read 1.342 GB + write 0.2545 GB per launch (profiles/r1_d_2d_2048_P2_direct.txt)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_p2, "launch_ms": p2_ms},
             "apply_roofline": {"algorithmic_bytes_per_apply": 568.0 * N, "achieved": 568.0 * N / (ms / args.steps * 1e-3) / 1e9,
                                "frac": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs":
