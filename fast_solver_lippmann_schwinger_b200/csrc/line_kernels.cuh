@@ -14,6 +14,7 @@
 //                   strided lines (es large, ls == 1) are read/written as 128-byte segments.
 #pragma once
 #include "fft_engine.cuh"
+#include <cooperative_groups.h>
 
 namespace lsk {
 using namespace lsfft;
@@ -268,6 +269,110 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     for (int a = 0; a < AR; ++a) o[(long)(a * T) * la.out_es] = acc[a];
 #pragma unroll
     for (int a = AR; a < E; ++a) o[(long)(a * T) * la.out_es] = accs[(a - AR) * TH];
+}
+
+// ---- middle, fused, one sub-transform per CTA, four CTAs per line group as a thread-block cluster ------
+// The four sub-transforms r = 0..3 of a padded line are independent until the final sum.  Giving
+// each its own CTA removes the two register-hungry pieces of k_mid_fused - the persistent copy of
+// the input line and the 16 accumulators carried across r - so three to four CTAs fit per SM instead
+// of two (the FP64 and shared-memory phases of different CTAs then overlap much better).  The four
+// partial results meet through distributed shared memory: every CTA parks its demodulated line in
+// its own smem, cluster.sync(), then CTA c sums quarter c of the line over the four ranks in a fixed
+// order (deterministic) and stores it.
+// grid = 4 * (lines / LPC), cluster (4,1,1); cluster rank = r.
+template <int N, bool MODE_B, int MINB>
+__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MINB)
+k_mid_cluster(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB,
+              const LineAddr la, long line0) {
+    namespace cg = cooperative_groups;
+    typedef Map<N, MODE_B> M;
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
+    constexpr int TH = MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
+    constexpr int UNIT = MODE_B ? 8 * N : N;
+    extern __shared__ __align__(128) cd sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    M mp;
+    cd* ex = sm + sm_group_off(mp);
+    cd* tw1 = sm + LPC * N;
+    load_tw1<N>(tw1, TAB);
+    const long Lcta = line0 + (long)(blockIdx.x >> 2) * LPC;
+    const long L = Lcta + mp.line;
+    const int t = mp.t;
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    cd v[E];
+    {
+        const cd* p = in + line_in(la, L) + (long)t * la.in_es;
+#pragma unroll
+        for (int a = 0; a < E; ++a) v[a] = p[(long)(a * T) * la.in_es];
+    }
+    __syncthreads();   // tw1 visible
+    const cd* g = MODE_B ? G + (((Lcta >> 3) + (mp.line >> 3)) * 4 + r) * (long)UNIT + mp.lay_lam()
+                         : G + ((Lcta + mp.line) * 4 + r) * (long)UNIT;
+    constexpr int gs = MODE_B ? 8 : 1;
+    {
+        cd gv[E];
+        fft_fwd<N>(v, t, r, ex, mp.lay, tw, [&]() {
+#pragma unroll
+            for (int e = 0; e < E; ++e) gv[e] = __ldg(&g[(long)(t + T * e) * gs]);
+        });
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], gv[e]);
+    }
+    fft_inv<N>(v, t, r, ex, mp.lay, tw);
+    if (r != 0) {
+#pragma unroll
+        for (int a = 1; a < E; ++a) v[a] = cmulc(v[a], c64(r * a * (16 / E)));
+    }
+    __syncthreads();   // everyone is done reading the exchange buffer: reuse it for the partial line
+    // park: element index within the CTA = line*N + j (mode A) / (grp*8N + j*8 + lam) (mode B)
+#pragma unroll
+    for (int a = 0; a < E; ++a) {
+        const int j = a * T + t;
+        const int idx = MODE_B ? (sm_group_off(mp) + j * 8 + mp.lay_lam()) : (mp.line * N + j);
+        sm[idx] = v[a];
+    }
+    cluster.sync();
+    // quarter r of the CTA's LPC*N points: sum the four ranks in the order 0,1,2,3
+    const cd* part[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[q] = cluster.map_shared_rank(sm, q);
+    constexpr int QUART = LPC * N / 4;
+    for (int i = threadIdx.x; i < QUART; i += TH) {
+        const int idx = r * QUART + i;
+        cd s0 = part[0][idx];
+        const cd s1 = part[1][idx], s2 = part[2][idx], s3 = part[3][idx];
+        s0 = cadd(cadd(cadd(s0, s1), s2), s3);
+        int line, j;
+        if (MODE_B) { const int w = idx % (8 * N); line = (idx / (8 * N)) * 8 + (w & 7); j = w >> 3; }
+        else { line = idx / N; j = idx % N; }
+        out[line_out(la, Lcta + line) + (long)j * la.out_es] = s0;
+    }
+    cluster.sync();    // keep every CTA's shared memory alive until its peers have read it
+}
+
+template <int N, bool B, int MINB>
+inline cudaError_t launch_mid_cluster(cudaStream_t s, long nlines, const cd* in, cd* out, const cd* G, const cd* TAB,
+                                      const LineAddr& la) {
+    constexpr int smem = Smem<N, B>::fwd_bytes;
+    constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_mid_cluster<N, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(4 * (nlines / LPC)));
+    cfg.blockDim = dim3(TH);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_mid_cluster<N, B, MINB>, in, out, G, TAB, la, (long)0);
 }
 
 // ---- middle, fused, two sub-transforms in flight (mode A, spectrum straight from HBM) ----------------

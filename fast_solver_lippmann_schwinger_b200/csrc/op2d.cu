@@ -95,6 +95,19 @@ template <int N> int launch_mid(Op2D* op) {
     // registers (0.706 ms), 0 = spectrum staged in shared memory by TMA bulk copies (0.761 ms)
     if (variant < 0) { const char* e = getenv("LS_P2_VARIANT"); variant = e ? atoi(e) : 1; }
     if (variant == 0) return launch_mid_v<N, true, 1>(op);
+    // experiment kept for the record: one sub-transform per CTA, thread-block cluster of 4, DSMEM reduction
+    // (3-4 CTAs/SM, no spills, bit-identical result - but 1.05-1.08 ms at 2048^2: two cluster.sync() per CTA and
+    // four times the per-CTA fixed costs outweigh the better pipe overlap)
+    if constexpr (N == 2048) if (variant == 6 || variant == 7) {
+        op->phase_begin(1);
+        const LineAddr la{1L << 40, 1, 0, op->ne, op->m, 0, 1};
+        cudaError_t e = (variant == 6) ? launch_mid_cluster<N, false, 3>(op->stream, op->ne, op->d_A, op->d_C, op->d_G, op->d_TABm, la)
+                                       : launch_mid_cluster<N, false, 4>(op->stream, op->ne, op->d_A, op->d_C, op->d_G, op->d_TABm, la);
+        op->phase_end();
+        op->launches++;
+        LS_CUDA_TRY(e);
+        return LS_OK;
+    }
     // experiment kept for the record (profiles/r1_b_notes.md): two sub-transforms in flight per thread;
     // correct, but 255 registers + 590 B of spills make it slower (0.92 ms) - instantiated for 2048 only
     if constexpr (N == 2048) { if (variant == 5) return launch_mid_dual<N, 4>(op); }
