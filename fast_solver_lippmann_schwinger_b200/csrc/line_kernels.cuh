@@ -271,6 +271,94 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     for (int a = AR; a < E; ++a) o[(long)(a * T) * la.out_es] = accs[(a - AR) * TH];
 }
 
+// ---- middle, fused, persistent CTAs with an asynchronously prefetched input line (mode A) -------------
+// Same arithmetic as k_mid_fused (spectrum straight from HBM, requested before the last butterfly stage).
+// A CTA walks over line groups with stride gridDim.x; while it transforms one group, the next group's
+// (strided, 16-byte-granular) input line is already on its way into the other half of a double buffer by
+// cp.async - thread-private, so no barrier is needed - and the engine tables are set up once per CTA.
+// smem: [exchange: LPC*N][x buffer 0: LPC*N][x buffer 1: LPC*N][tw1]
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+template <int N>
+__global__ void __launch_bounds__(GeoA<N>::THREADS, GeoA<N>::THREADS <= 128 ? 2 : 1)
+k_mid_persist(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB,
+              const LineAddr la, long ngroups) {
+    typedef Map<N, false> M;
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
+    extern __shared__ __align__(128) cd sm[];
+    M mp;
+    cd* ex = sm;
+    cd* xbuf0 = sm + LPC * N;
+    cd* xbuf1 = sm + 2 * LPC * N;
+    cd* tw1 = sm + 3 * LPC * N;
+    load_tw1<N>(tw1, TAB);
+    const int t = mp.t;
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    auto issue_x = [&](long grp, cd* xb) {
+        const cd* p = in + line_in(la, grp * LPC + mp.line) + (long)t * la.in_es;
+#pragma unroll
+        for (int a = 0; a < E; ++a) cp_async16(&xb[mp.lay.phys(a * T + t)], p + (long)(a * T) * la.in_es);
+        cp_async_commit();
+    };
+    long grp = blockIdx.x;
+    if (grp < ngroups) issue_x(grp, xbuf0);
+    __syncthreads();   // tw1 visible
+    int it = 0;
+#pragma unroll 1
+    for (; grp < ngroups; grp += gridDim.x, ++it) {
+        cd* xs = (it & 1) ? xbuf1 : xbuf0;
+        const long nxt = grp + gridDim.x;
+        if (nxt < ngroups) {
+            issue_x(nxt, (it & 1) ? xbuf0 : xbuf1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        const long L = grp * LPC + mp.line;
+        const cd* g = G + (L * 4) * (long)N + t;
+        cd acc[E];
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            cd v[E];
+#pragma unroll
+            for (int a = 0; a < E; ++a) v[a] = xs[mp.lay.phys(a * T + t)];
+            cd gv[E];
+            const cd* gr = g + (long)r * N;
+            fft_fwd<N>(v, t, r, ex, mp.lay, tw, [&]() {
+#pragma unroll
+                for (int e = 0; e < E; ++e) gv[e] = __ldg(&gr[T * e]);
+            });
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], gv[e]);
+            fft_inv<N>(v, t, r, ex, mp.lay, tw);
+            demod_accumulate<N>(acc, v, r);
+        }
+        cd* o = out + line_out(la, L) + (long)t * la.out_es;
+#pragma unroll
+        for (int a = 0; a < E; ++a) o[(long)(a * T) * la.out_es] = acc[a];
+    }
+}
+
+template <int N>
+inline cudaError_t launch_mid_persist(cudaStream_t s, long nlines, const cd* in, cd* out, const cd* G, const cd* TAB,
+                                      const LineAddr& la, int ctas) {
+    constexpr int smem = (3 * GeoA<N>::LPC * N + EngTab<N>::TW1N) * (int)sizeof(cd);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_mid_persist<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const long ngroups = nlines / GeoA<N>::LPC;
+    const long grid = ngroups < ctas ? ngroups : ctas;
+    k_mid_persist<N><<<(unsigned)grid, GeoA<N>::THREADS, smem, s>>>(in, out, G, TAB, la, ngroups);
+    return cudaPeekAtLastError();
+}
+
 // ---- middle, fused, one sub-transform per CTA, four CTAs per line group as a thread-block cluster ------
 // The four sub-transforms r = 0..3 of a padded line are independent until the final sum.  Giving
 // each its own CTA removes the two register-hungry pieces of k_mid_fused - the persistent copy of

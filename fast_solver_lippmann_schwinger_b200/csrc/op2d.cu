@@ -95,6 +95,18 @@ template <int N> int launch_mid(Op2D* op) {
     // registers (0.706 ms), 0 = spectrum staged in shared memory by TMA bulk copies (0.761 ms)
     if (variant < 0) { const char* e = getenv("LS_P2_VARIANT"); variant = e ? atoi(e) : 1; }
     if (variant == 0) return launch_mid_v<N, true, 1>(op);
+    // experiment kept for the record: persistent CTAs, next input line prefetched by cp.async (0.714-0.720 ms)
+    if constexpr (N == 2048) if (variant == 8) {
+        static int ctas = -1;
+        if (ctas < 0) { const char* e = getenv("LS_P2_CTAS"); ctas = e ? atoi(e) : 2 * 148; }
+        op->phase_begin(1);
+        cudaError_t e = launch_mid_persist<N>(op->stream, op->ne, op->d_A, op->d_C, op->d_G, op->d_TABm,
+                                              LineAddr{1L << 40, 1, 0, op->ne, op->m, 0, 1}, ctas);
+        op->phase_end();
+        op->launches++;
+        LS_CUDA_TRY(e);
+        return LS_OK;
+    }
     // experiment kept for the record: one sub-transform per CTA, thread-block cluster of 4, DSMEM reduction
     // (3-4 CTAs/SM, no spills, bit-identical result - but 1.05-1.08 ms at 2048^2: two cluster.sync() per CTA and
     // four times the per-CTA fixed costs outweigh the better pipe overlap)
