@@ -135,7 +135,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(n),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.WORKERS, "kind": "port",
@@ -151,6 +151,7 @@ def workload_config(n):
     return {"workload": "2-D Greengard_Vico LS operator apply, grid %dx%d (padded %dx%d), k=2pi/(10h), "
                         "Gaussian-bump contrast (examples/example.jl:48), rng(1234) complex input" % (n, n, 4 * n, 4 * n),
             "grid": [n, n], "padded": [4 * n, 4 * n], "quadRule": "Greengard_Vico", "points_per_wavelength": 10,
+            "element": "complex128 (two f64)",
             "l2_policy": "inputs larger than L2 (spectrum %.2f GB, intermediates %.2f GB each per apply)" % (
                 16 * 16 * n * n / 1e9, 64 * n * n / 1e9),
             "parallelism": "replica per GPU (2-D path does not shard)"}
@@ -419,7 +420,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(n),
             "e2e": {"value": world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N,
                     "d2h_bytes_per_step": 16 * N, "steps": e2e_steps, "api": "fastconvolution(FastM, b) on pinned host arrays"},
