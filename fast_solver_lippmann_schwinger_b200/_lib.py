@@ -91,6 +91,7 @@ def lib():
         "ls_spm_mv": (ci, [vp, CDouble, vp, CDouble, vp, ci]),
         "ls_spm_info": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(ci), C.POINTER(ci)]),
         "ls_krylov_create": (ci, [C.POINTER(vp), i64]),
+        "ls_krylov_set_orth": (ci, [vp, ci]),
         "ls_zdotc": (ci, [vp, vp, vp, C.POINTER(CDouble)]),
         "ls_dznrm2": (ci, [vp, vp, C.POINTER(dbl)]),
         "ls_zaxpy": (ci, [vp, CDouble, vp, vp]),

@@ -142,6 +142,93 @@ k_axpy_nrm2(const cd* __restrict__ vprev, const double* hprev_re, const double* 
     block_finish(sx, 0.0, partials, ticket, out, nullptr, take_sqrt);
 }
 
+// ---- classical Gram-Schmidt (orth_meth = ClassicalGramSchmidt / DGKS upstream): BLAS-2 style sweeps ----
+constexpr int KC = 8;     // columns per multi-dot pass
+
+// h[c0 + i] = conj(V[:, c0 + i]) . w for i < kc <= KC, one sweep over w and kc columns
+__global__ void __launch_bounds__(RED_THREADS)
+k_multi_dot(const cd* __restrict__ V, long ldv, int c0, int kc, const cd* __restrict__ w, long n,
+            double2* partials /* [KC][gridDim.x] */, unsigned* ticket, double* out /* 2*(c0+i) */) {
+    double sx[KC], sy[KC];
+#pragma unroll
+    for (int i = 0; i < KC; ++i) { sx[i] = 0.0; sy[i] = 0.0; }
+    for (long e = (long)blockIdx.x * RED_THREADS + threadIdx.x; e < n; e += (long)gridDim.x * RED_THREADS) {
+        const cd b = w[e];
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+            if (i < kc) {
+                const cd a = V[e + (long)(c0 + i) * ldv];
+                sx[i] += a.x * b.x + a.y * b.y;
+                sy[i] += a.x * b.y - a.y * b.x;
+            }
+        }
+    }
+    __shared__ double shx[KC][RED_THREADS / 32], shy[KC][RED_THREADS / 32];
+    __shared__ bool is_last;
+    const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+        const double a = warp_sum(sx[i]), b = warp_sum(sy[i]);
+        if (l == 0) { shx[i][wp] = a; shy[i][wp] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < KC) {
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < RED_THREADS / 32; ++q) { a += shx[threadIdx.x][q]; b += shy[threadIdx.x][q]; }
+        partials[(long)threadIdx.x * gridDim.x + blockIdx.x] = make_double2(a, b);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tk = atomicInc(ticket, gridDim.x - 1);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int i = 0; i < kc; ++i) {
+            double ax = 0.0, ay = 0.0;
+            for (int q = threadIdx.x; q < (int)gridDim.x; q += RED_THREADS) {
+                const double2 p = __ldcg(&partials[(long)i * gridDim.x + q]);
+                ax += p.x;
+                ay += p.y;
+            }
+            ax = warp_sum(ax);
+            ay = warp_sum(ay);
+            __syncthreads();
+            if (l == 0) { shx[0][wp] = ax; shy[0][wp] = ay; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tx = 0.0, ty = 0.0;
+                for (int q = 0; q < RED_THREADS / 32; ++q) { tx += shx[0][q]; ty += shy[0][q]; }
+                out[2 * (c0 + i)] = tx;
+                out[2 * (c0 + i) + 1] = ty;
+            }
+        }
+    }
+}
+
+// w -= sum_{i<k} h_i V_i ;  out = sqrt(sum |w|^2)   (h: k complex values on the device)
+__global__ void __launch_bounds__(RED_THREADS)
+k_multi_axpy_nrm2(const cd* __restrict__ V, long ldv, int k, const double* __restrict__ h, cd* w, long n,
+                  double2* partials, unsigned* ticket, double* out, int take_sqrt) {
+    __shared__ double hs[128];
+    for (int i = threadIdx.x; i < 2 * k; i += RED_THREADS) hs[i] = h[i];
+    __syncthreads();
+    double sx = 0.0;
+    for (long e = (long)blockIdx.x * RED_THREADS + threadIdx.x; e < n; e += (long)gridDim.x * RED_THREADS) {
+        cd ww = w[e];
+        for (int i = 0; i < k; ++i) {
+            const cd p = V[e + (long)i * ldv];
+            ww.x -= hs[2 * i] * p.x - hs[2 * i + 1] * p.y;
+            ww.y -= hs[2 * i] * p.y + hs[2 * i + 1] * p.x;
+        }
+        w[e] = ww;
+        sx += ww.x * ww.x + ww.y * ww.y;
+    }
+    block_finish(sx, 0.0, partials, ticket, out, nullptr, take_sqrt);
+}
+
 // y += alpha*x  (alpha by value)
 __global__ void __launch_bounds__(256)
 k_axpy(cd alpha, const cd* __restrict__ x, cd* y, long n) {
@@ -260,6 +347,66 @@ struct Krylov : HandleBase {
         launches++;
         return LS_OK;
     }
+
+    // orth_meth: 0 ModifiedGramSchmidt (default, what the reference's call sites use), 1 ClassicalGramSchmidt,
+    // 2 DGKS (classical + conditional re-orthogonalisation) - IterativeSolvers.jl orthogonalize.jl
+    int orth_meth = 0;
+    double2* d_partials_multi = nullptr;
+    double* d_corr = nullptr;
+    int multi_dot(const cd* V, long ldv, int k, const cd* w, double* out, cudaStream_t s) {
+        for (int c0 = 0; c0 < k; c0 += KC) {
+            const int kc = (k - c0) < KC ? (k - c0) : KC;
+            k_multi_dot<<<RED_BLOCKS, RED_THREADS, 0, s>>>(V, ldv, c0, kc, w, n, d_partials_multi, d_ticket, out);
+            launches++;
+        }
+        return allreduce(out, 2 * k, s);
+    }
+    // classical Gram-Schmidt (+ DGKS) of w against V[:,0..k-1] and normalisation; h lands in d_scal
+    int cgs(const cd* V, long ldv, int k, cd* w, cudaStream_t s) {
+        double* h = d_scal;
+        int rc;
+        if ((rc = multi_dot(V, ldv, k, w, h, s))) return rc;
+        k_multi_axpy_nrm2<<<RED_BLOCKS, RED_THREADS, 0, s>>>(V, ldv, k, h, w, n, d_partials, d_ticket, h + 2 * k, comm ? 0 : 1);
+        launches++;
+        if ((rc = finish_norm(h + 2 * k, s))) return rc;
+        cudaMemsetAsync(h + 2 * k + 1, 0, sizeof(double), s);
+        if (orth_meth == 2) {
+            std::vector<double> hh(2 * (size_t)k + 2), cc(2 * (size_t)k + 2);
+            LS_CUDA_TRY(cudaMemcpyAsync(h_scal, h, (2 * (size_t)k + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            LS_CUDA_TRY(cudaStreamSynchronize(s));
+            memcpy(hh.data(), h_scal, (2 * (size_t)k + 1) * sizeof(double));
+            double nrm = hh[2 * k], proj = 0.0;
+            for (int i = 0; i < 2 * k; ++i) proj += hh[i] * hh[i];
+            proj = sqrt(proj);
+            const double eta = 1.0 / sqrt(2.0);
+            bool changed = false;
+            while (nrm < eta * proj) {
+                if ((rc = multi_dot(V, ldv, k, w, d_corr, s))) return rc;
+                k_multi_axpy_nrm2<<<RED_BLOCKS, RED_THREADS, 0, s>>>(V, ldv, k, d_corr, w, n, d_partials, d_ticket, d_corr + 2 * k, comm ? 0 : 1);
+                launches++;
+                if ((rc = finish_norm(d_corr + 2 * k, s))) return rc;
+                LS_CUDA_TRY(cudaMemcpyAsync(h_scal, d_corr, (2 * (size_t)k + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+                LS_CUDA_TRY(cudaStreamSynchronize(s));
+                memcpy(cc.data(), h_scal, (2 * (size_t)k + 1) * sizeof(double));
+                proj = 0.0;
+                for (int i = 0; i < 2 * k; ++i) { proj += cc[i] * cc[i]; hh[i] += cc[i]; }
+                proj = sqrt(proj);
+                nrm = cc[2 * k];
+                changed = true;
+            }
+            if (changed) {
+                hh[2 * k] = nrm; hh[2 * k + 1] = 0.0;
+                memcpy(h_scal + 144, hh.data(), (2 * (size_t)k + 2) * sizeof(double));     // pinned scratch beyond the live part
+                LS_CUDA_TRY(cudaMemcpyAsync(h, h_scal + 144, (2 * (size_t)k + 2) * sizeof(double), cudaMemcpyHostToDevice, s));
+            }
+        }
+        k_scal_inv_dev<<<grid_stream(n), 256, 0, s>>>(h + 2 * k, w, n);
+        launches++;
+        return LS_OK;
+    }
+    int orthogonalize(const cd* V, long ldv, int k, cd* w, cudaStream_t s) {
+        return (orth_meth == 0 || k == 0) ? mgs(V, ldv, k, w, s) : cgs(V, ldv, k, w, s);
+    }
 };
 
 int krylov_alloc(Krylov* K, long n) {
@@ -268,9 +415,11 @@ int krylov_alloc(Krylov* K, long n) {
     if ((rc = K->dmalloc((void**)&K->d_partials, RED_BLOCKS * sizeof(double2)))) return rc;
     if ((rc = K->dmalloc((void**)&K->d_ticket, sizeof(unsigned)))) return rc;
     if ((rc = K->dmalloc((void**)&K->d_scal, 2 * 72 * sizeof(double)))) return rc;
+    if ((rc = K->dmalloc((void**)&K->d_corr, 2 * 72 * sizeof(double)))) return rc;
+    if ((rc = K->dmalloc((void**)&K->d_partials_multi, (size_t)KC * RED_BLOCKS * sizeof(double2)))) return rc;
     if ((rc = K->dmalloc((void**)&K->d_y, 64 * sizeof(cd)))) return rc;
     LS_CUDA_TRY(cudaMemsetAsync(K->d_ticket, 0, sizeof(unsigned), K->stream));
-    LS_CUDA_TRY(cudaMallocHost((void**)&K->h_scal, 2 * 72 * sizeof(double)));
+    LS_CUDA_TRY(cudaMallocHost((void**)&K->h_scal, 4 * 72 * sizeof(double)));
     K->host_allocs.push_back(K->h_scal);
     LS_CUDA_TRY(cudaStreamSynchronize(K->stream));
     return LS_OK;
@@ -343,6 +492,14 @@ int ls_krylov_create(ls_handle* out, int64_t n) {
     LS_REQUIRE(K->kind == KIND_VEC, LS_ERR_INVALID, fn ": not a Krylov workspace handle");     \
     LS_CUDA_TRY(cudaSetDevice(K->device))
 
+int ls_krylov_set_orth(ls_handle h, int orth_meth) {
+    KRYLOV_HANDLE(K, h, "ls_krylov_set_orth");
+    LS_REQUIRE(orth_meth >= 0 && orth_meth <= 2, LS_ERR_INVALID,
+               "ls_krylov_set_orth: 0 ModifiedGramSchmidt, 1 ClassicalGramSchmidt, 2 DGKS");
+    K->orth_meth = orth_meth;
+    return LS_OK;
+}
+
 int ls_zdotc(ls_handle h, const ls_cdouble* x, const ls_cdouble* y, ls_cdouble* result) {
     KRYLOV_HANDLE(K, h, "ls_zdotc");
     LS_REQUIRE(x && y && result, LS_ERR_INVALID, "ls_zdotc: null pointer");
@@ -386,7 +543,7 @@ int ls_mgs_step(ls_handle h, const ls_cdouble* V, int64_t ldv, int k, ls_cdouble
     KRYLOV_HANDLE(K, h, "ls_mgs_step");
     LS_REQUIRE(V && w && hcol, LS_ERR_INVALID, "ls_mgs_step: null pointer");
     LS_REQUIRE(k >= 0 && k <= 64 && ldv >= K->n, LS_ERR_INVALID, "ls_mgs_step: k must be in [0,64] and ldv >= n");
-    { int rc = K->mgs((const cd*)V, ldv, k, (cd*)w, K->stream); if (rc) return rc; }
+    { int rc = K->orthogonalize((const cd*)V, ldv, k, (cd*)w, K->stream); if (rc) return rc; }
     LS_CUDA_TRY(cudaGetLastError());
     LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, 2 * (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, K->stream));
     LS_CUDA_TRY(cudaStreamSynchronize(K->stream));
@@ -511,7 +668,7 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
         if (rc) return rc;
         mv++;
         // orthogonalize_and_normalize! (modified Gram-Schmidt), Hessenberg column -> host
-        rc = K->mgs(V, ldv, k, w, s);
+        rc = K->orthogonalize(V, ldv, k, w, s);
         if (rc) return rc;
         LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, 2 * (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
         LS_CUDA_TRY(cudaStreamSynchronize(s));

@@ -179,8 +179,11 @@ class KrylovWorkspace(_Handle):
         return h
 
 
+ORTH_METHODS = {"ModifiedGramSchmidt": 0, "ClassicalGramSchmidt": 1, "DGKS": 2}
+
+
 def gmres_(x, A, b, Pl=None, abstol=0.0, reltol=None, restart=None, maxiter=None, log=False,
-           initially_zero=False, workspace=None):
+           initially_zero=False, workspace=None, orth_meth="ModifiedGramSchmidt"):
     """``gmres!(x, A, b; Pl, abstol, reltol, restart, maxiter, log, initially_zero)``.
 
     A is a GPU operator (FastM / FastM3D); Pl is None (Identity) or a SparsifyingPreconditioner.
@@ -191,6 +194,9 @@ def gmres_(x, A, b, Pl=None, abstol=0.0, reltol=None, restart=None, maxiter=None
     restart = min(20, N) if restart is None else int(restart)
     maxiter = getattr(A, "N_global", N) if maxiter is None else int(maxiter)
     ws = workspace if workspace is not None else KrylovWorkspace(N)
+    if orth_meth not in ORTH_METHODS:
+        raise ValueError("orth_meth must be one of %s" % sorted(ORTH_METHODS))
+    check(lib().ls_krylov_set_orth(ws.handle, ORTH_METHODS[orth_meth]))
     dev = isinstance(x, DeviceBuffer)
     if dev != isinstance(b, DeviceBuffer):
         raise TypeError("x and b must both be DeviceBuffer or both numpy arrays")

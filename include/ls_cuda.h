@@ -123,6 +123,10 @@ int ls_spm_info(ls_handle A, int64_t* nrows, int64_t* ncols, int64_t* nnz, int* 
  * examples/example.jl:85,91).  A Krylov workspace owns the reduction buffers for vectors of
  * length n.  All vector pointers below are DEVICE pointers (ls_dev_alloc).                  */
 int ls_krylov_create(ls_handle* out, int64_t n);
+/* orth_meth keyword of gmres! (IterativeSolvers.jl orthogonalize.jl): 0 ModifiedGramSchmidt (upstream default,
+ * used by every call site of the reference), 1 ClassicalGramSchmidt, 2 DGKS.  1 and 2 sweep the basis with
+ * BLAS-2 style multi-dot / multi-axpy kernels: half the HBM traffic of the Gram-Schmidt step.              */
+int ls_krylov_set_orth(ls_handle k, int orth_meth);
 int ls_zdotc(ls_handle k, const ls_cdouble* x, const ls_cdouble* y, ls_cdouble* result);   /* sum conj(x) y */
 int ls_dznrm2(ls_handle k, const ls_cdouble* x, double* result);
 int ls_zaxpy(ls_handle k, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble* y);           /* y += alpha x */

@@ -61,8 +61,35 @@ def solve_least_squares(H, beta, k):
     return y
 
 
+def _orthogonalize(V, k, w, orth_meth):
+    """orthogonalize.jl ``orthogonalize_and_normalize!``: returns (h[0:k], nrm, w/nrm)."""
+    if orth_meth == "ModifiedGramSchmidt":
+        h = np.zeros(k, dtype=np.complex128)
+        for i in range(k):
+            h[i] = np.vdot(V[:, i], w)
+            w = w - h[i] * V[:, i]
+        nrm = np.linalg.norm(w)
+        return h, nrm, w * (1.0 / nrm)
+    Vk = V[:, :k]
+    h = Vk.conj().T @ w                          # mul!(h, adjoint(V), w)
+    w = w - Vk @ h                               # mul!(w, V, h, -1, 1)
+    nrm = np.linalg.norm(w)
+    if orth_meth == "DGKS":
+        eta = 1.0 / np.sqrt(2.0)
+        projection_size = np.linalg.norm(h)
+        while nrm < eta * projection_size:
+            correction = Vk.conj().T @ w
+            projection_size = np.linalg.norm(correction)
+            w = w - Vk @ correction
+            h = h + correction
+            nrm = np.linalg.norm(w)
+    elif orth_meth != "ClassicalGramSchmidt":
+        raise ValueError(orth_meth)
+    return h, nrm, w * (1.0 / nrm)
+
+
 def gmres(x, A_mul, b, Pl_ldiv=None, abstol=0.0, reltol=None, restart=None, maxiter=None,
-          initially_zero=False):
+          initially_zero=False, orth_meth="ModifiedGramSchmidt"):
     """``gmres!(x, A, b; Pl, abstol, reltol, restart, maxiter, log=true)``.
 
     ``A_mul(v) -> A v``; ``Pl_ldiv(v) -> Pl^-1 v`` (None = Identity).
@@ -104,14 +131,11 @@ def gmres(x, A_mul, b, Pl_ldiv=None, abstol=0.0, reltol=None, restart=None, maxi
         # expand!
         w = pl(A_mul(V[:, k - 1]))
         mv += 1
-        # orthogonalize_and_normalize!  (ModifiedGramSchmidt)
-        for i in range(k):
-            hik = np.vdot(V[:, i], w)
-            H[i, k - 1] = hik
-            w = w - hik * V[:, i]
-        nrm = np.linalg.norm(w)
+        # orthogonalize_and_normalize!  (ModifiedGramSchmidt unless asked otherwise)
+        hcol, nrm, wn = _orthogonalize(V, k, w, orth_meth)
+        H[:k, k - 1] = hcol
         H[k, k - 1] = nrm
-        V[:, k] = w * (1.0 / nrm)
+        V[:, k] = wn
         # update_residual!
         nullvec[k] = -np.conj(np.vdot(nullvec[:k], H[:k, k - 1]) / H[k, k - 1])
         accumulator += abs(nullvec[k]) ** 2

@@ -202,3 +202,38 @@ def test_plasma_contrast_preconditioned_solve():
     m = min(50, len(hist_o))
     assert np.max(np.abs(hg["resnorm"][:m] - hist_o[:m]) / hist_o[:m]) < 1e-8
     assert _rel(xg, xo) < 1e-7
+
+
+@pytest.mark.parametrize("orth", ["ClassicalGramSchmidt", "DGKS"])
+def test_gmres_other_orthogonalisations(orth):
+    """orth_meth = ClassicalGramSchmidt / DGKS (IterativeSolvers.jl options; BLAS-2 style sweeps on the GPU)."""
+    from oracle import ls_oracle as O
+    from oracle.gmres_is import gmres as gmres_oracle
+    import fast_solver_lippmann_schwinger_b200 as ls
+    n = 64
+    x, h, k, Mo = O.pow2_problem_2d(n, ppw=6.0, nu=lambda X, Y: 4.0 * O.nu_gaussian_2d(X, Y))
+    N = n * n
+    Mg = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.n, Mo.m, Mo.omega, quadRule="Greengard_Vico")
+    rng = np.random.default_rng(21)
+    rhs = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    xo = np.zeros(N, complex)
+    xo, hist_o, conv_o, mv_o = gmres_oracle(xo, lambda v: O.fastconvolution(Mo, v), rhs, maxiter=45, reltol=1e-10, orth_meth=orth)
+    xg = np.zeros(N, complex)
+    xg, hg = ls.gmres_(xg, Mg, rhs, maxiter=45, reltol=1e-10, log=True, orth_meth=orth)
+    assert hg.iters == len(hist_o) and hg.mvps == mv_o
+    assert np.max(np.abs(hg["resnorm"] - hist_o) / hist_o) < 1e-8
+    assert _rel(xg, xo) < 1e-8
+    # and a plain multi-column step against numpy (k = 11 crosses the 8-column pass boundary)
+    K = ls.KrylovWorkspace(N)
+    from fast_solver_lippmann_schwinger_b200._lib import check, lib
+    check(lib().ls_krylov_set_orth(K.handle, 1 if orth == "ClassicalGramSchmidt" else 2))
+    Q, _ = np.linalg.qr(rng.standard_normal((N, 11)) + 1j * rng.standard_normal((N, 11)))
+    w = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    dV = ls.DeviceBuffer.from_host(np.asfortranarray(Q).reshape(-1, order="F"))
+    dw = ls.DeviceBuffer.from_host(w)
+    hcol = K.mgs_step(dV, N, 11, dw)
+    href = Q.conj().T @ w
+    wr = w - Q @ href
+    assert np.abs(hcol[:11] - href).max() < 1e-12 * np.abs(href).max()
+    assert abs(hcol[11] - np.linalg.norm(wr)) < 1e-12 * np.linalg.norm(wr)
+    assert _rel(dw.to_host(), wr / np.linalg.norm(wr)) < 1e-12
