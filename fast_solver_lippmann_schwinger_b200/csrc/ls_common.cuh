@@ -44,6 +44,7 @@ struct HandleBase {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
+    cd* stage_b = nullptr; cd* stage_y = nullptr;   // device staging for host-pointer applies (lazily allocated)
     std::vector<void*> dev_allocs;    // everything cudaMalloc'ed by the handle
     std::vector<void*> host_allocs;   // pinned staging
 

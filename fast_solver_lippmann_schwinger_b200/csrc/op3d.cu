@@ -18,6 +18,7 @@
 #include "ls_common.cuh"
 #include "line_kernels.cuh"
 #include "dist.cuh"
+#include "gv_spectrum.cuh"
 
 using namespace ls;
 using namespace lsk;
@@ -52,23 +53,8 @@ struct GenParams {
     double scale;
 };
 
-// Gtruncated3D (Functions.jl:49-51) at |(kx,ky,kz)|, numpy-sinc argument path of the oracle
 __device__ __forceinline__ cd gtrunc3d(double s, const GenParams& p) {
-    const double PI = 3.141592653589793;
-    const double Ls = p.L * s;
-    const double c = cos(Ls);
-    double sinc;
-    {
-        const double xs = Ls / PI;
-        const double yv = PI * xs;
-        sinc = (xs == 0.0) ? 1.0 : sin(yv) / yv;
-    }
-    // -1 + e^{iLk} (c - i k L sinc)
-    const double ar = c, ai = -(p.k * p.L * sinc);
-    const double nr = -1.0 + (p.eLk_re * ar - p.eLk_im * ai);
-    const double ni = p.eLk_re * ai + p.eLk_im * ar;
-    const double den = p.k * p.k - s * s;
-    return make_double2(nr / den, ni / den);
+    return gtrunc3d_eval(s, p.L, p.k, p.eLk_re, p.eLk_im);
 }
 
 // fills the device spectrum in its final layout, either by gathering from the reference-ordered
@@ -92,11 +78,7 @@ __global__ void k_fill_g3d(const cd* __restrict__ gin, cd* __restrict__ gout, co
         if (gin != nullptr) {
             v = gin[ix + p.ne * (iy + p.me * iz)];
         } else {
-            const double kxv = p.dk * (double)(ix - p.ne / 2);
-            const double kyv = p.dk * (double)(iy - p.me / 2);
-            const double kzv = p.dk * (double)(iz - p.le / 2);
-            const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv)), __dmul_rn(kzv, kzv));
-            v = gtrunc3d(sqrt(s2), p);
+            v = gtrunc3d(gv_radius(p.dk, ix, iy, iz, p.ne, p.me, p.le), p);
         }
         gout[idx] = make_double2(v.x * p.scale, v.y * p.scale);
     }
@@ -214,8 +196,13 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
     LS_REQUIRE(n == m, LS_ERR_INVALID,
                "ls_op3d_create: FFTconvolution pads (ne, ne, le): n must equal m (FastConvolution3D.jl:48)");
     auto ok3 = [](long v) { return v == 64 || v == 128 || v == 256 || v == 512; };
-    LS_REQUIRE(ok3(n) && ok3(m) && ok3(l), LS_ERR_UNSUPPORTED,
-               "ls_op3d_create: n=%ld m=%ld l=%ld - the GPU path serves powers of two in [64, 512]", (long)n, (long)m, (long)l);
+    if (!(ok3(n) && ok3(m) && ok3(l))) {
+        LS_REQUIRE(nranks == 1, LS_ERR_UNSUPPORTED,
+                   "ls_op3d_create_dist: n=%ld m=%ld l=%ld - the sharded path serves powers of two in [64, 512]", (long)n, (long)m, (long)l);
+        LS_REQUIRE(gfft != nullptr || (L > 0 && Lp > 0), LS_ERR_INVALID,
+                   "ls_op3d_create: pass GFFT or the Greengard-Vico parameters L, Lp to generate it on the device");
+        return create_op3d_generic(out, n, m, l, ne, me, le, nu, gfft, omega, L, Lp);     // any size: Bluestein lines
+    }
     LS_REQUIRE(gfft != nullptr || (L > 0 && Lp > 0), LS_ERR_INVALID,
                "ls_op3d_create: pass GFFT or the Greengard-Vico parameters L, Lp to generate it on the device");
     LS_REQUIRE(nranks == 1 || nranks == 2 || nranks == 4 || nranks == 8, LS_ERR_INVALID,
@@ -310,24 +297,24 @@ int ls_nccl_unique_id(void* out128) {
 
 int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc) {
     LS_REQUIRE(h && b && y, LS_ERR_INVALID, "ls_op3d_apply: null argument");
-    Op3D* op = reinterpret_cast<Op3D*>(h);
+    HandleBase* op = reinterpret_cast<HandleBase*>(h);      // power-of-two (Op3D) or general-size operator
     LS_REQUIRE(op->kind == KIND_OP3D, LS_ERR_INVALID, "ls_op3d_apply: not a 3-D operator handle");
     LS_REQUIRE(mode == LS_APPLY_FASTCONVOLUTION || mode == LS_APPLY_FFTCONVOLUTION, LS_ERR_INVALID,
                "ls_op3d_apply: unknown mode %d", mode);
     LS_CUDA_TRY(cudaSetDevice(op->device));
-    const size_t bytes = (size_t)op->n * op->m * op->lloc * sizeof(cd);
+    const size_t bytes = (size_t)op->op_size() * sizeof(cd);
     if (memloc == LS_MEM_DEVICE)
-        return apply_device3(op, reinterpret_cast<const cd*>(b), reinterpret_cast<cd*>(y), mode);
+        return op->apply_dev(reinterpret_cast<const cd*>(b), reinterpret_cast<cd*>(y), mode);
     LS_REQUIRE(memloc == LS_MEM_HOST, LS_ERR_INVALID, "ls_op3d_apply: unknown memloc %d", memloc);
-    if (!op->d_b) {
+    if (!op->stage_b) {
         int rc;
-        if ((rc = op->dmalloc((void**)&op->d_b, bytes))) return rc;
-        if ((rc = op->dmalloc((void**)&op->d_y, bytes))) return rc;
+        if ((rc = op->dmalloc((void**)&op->stage_b, bytes))) return rc;
+        if ((rc = op->dmalloc((void**)&op->stage_y, bytes))) return rc;
     }
-    LS_CUDA_TRY(cudaMemcpyAsync(op->d_b, b, bytes, cudaMemcpyHostToDevice, op->stream));
-    int rc = apply_device3(op, op->d_b, op->d_y, mode);
+    LS_CUDA_TRY(cudaMemcpyAsync(op->stage_b, b, bytes, cudaMemcpyHostToDevice, op->stream));
+    int rc = op->apply_dev(op->stage_b, op->stage_y, mode);
     if (rc) return rc;
-    LS_CUDA_TRY(cudaMemcpyAsync(y, op->d_y, bytes, cudaMemcpyDeviceToHost, op->stream));
+    LS_CUDA_TRY(cudaMemcpyAsync(y, op->stage_y, bytes, cudaMemcpyDeviceToHost, op->stream));
     LS_CUDA_TRY(cudaStreamSynchronize(op->stream));
     return LS_OK;
 }

@@ -88,7 +88,9 @@ int ls_op_size(ls_handle h, int64_t* N);
  * spectrum Gtruncated3D(L, k, |kappa|) (Functions.jl:49-51; grid kappa = (2 pi/Lp)(-2n:2n-1),
  * FastConvolution3D.jl:72-99) is then evaluated on the device straight into the kernel layout
  * (at 256^3 the array is 17 GB, at 512^3 137 GB - too big to ship from the host).
- * Served: n == m (the reference pads (ne, ne, le), :48), n, m, l in {64,128,256,512}.        */
+ * Served: n == m (the reference pads (ne, ne, le), :48).  Fast path: n, m, l in {64,128,256,512};
+ * any other size with 5n - 1 <= 4096 (examples/example3D.jl ships n = 48) runs on the general path
+ * (Bluestein lines, single GPU).                                                              */
 int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
                    const double* nu, const ls_cdouble* gfft_or_null, double omega, double L, double Lp,
                    int flags);

@@ -55,7 +55,7 @@ def test_3d_device_buffers_inplace_and_errors():
     with pytest.raises(ls.LSCudaError):          # n != m: the reference pads (ne, ne, le)
         ls.FastM3D(None, np.zeros(64 * 128 * 64), 256, 512, 256, 64, 128, 64, 1.0, L=1.0, Lp=4.0)
     with pytest.raises(ls.LSUnsupported):
-        ls.FastM3D(None, np.zeros(48 ** 3), 192, 192, 192, 48, 48, 48, 48.0, L=1.8, Lp=4.0)   # example3D.jl size: not a power of two
+        ls.FastM3D(None, np.zeros(900 * 900 * 2), 3600, 3600, 8, 900, 900, 2, 1.0, L=1.8, Lp=4.0)   # too long for the general path
 
 
 def test_long_z_lines_512():
@@ -105,3 +105,35 @@ def test_y_lines_512_properties():
     #  (FastConvolution3D.jl:72-79), so for l != n the kernel is not the free-space one - a reference
     #  quirk both the oracle and the device generator reproduce; the cubic case is checked in
     #  tests/test_gpu_fullsize.py)
+
+
+@pytest.mark.parametrize("n,l", [(48, 48), (20, 36)])
+def test_general_sizes_example3d_as_shipped(n, l):
+    """examples/example3D.jl:20-54 ships n = 48 (h = 1/48, k = 1/h, padded 192^3): the general-size path
+    (Bluestein lines), with the host spectrum and with the device-generated one."""
+    from oracle import ls_oracle as O
+    import fast_solver_lippmann_schwinger_b200 as ls
+    h = 1.0 / n
+    x = -0.5 + h * np.arange(n)
+    z = -0.5 * l / n + h * np.arange(l)
+    k = 1.0 / h
+    Mo = O.buildFastConvolution3D(x, x, z, h, k, O.nu_gaussian_3d)
+    Mg = ls.FastM3D(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.le, n, n, l, k)
+    N = n * n * l
+    rng = np.random.default_rng(48)
+    b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    y_ref = Mo * b
+    assert _rel(Mg * b, y_ref) <= TOL
+    assert _rel(ls.FFTconvolution(Mg, b), O.FFTconvolution3D(Mo, b)) <= TOL
+    Mgen = ls.FastM3D(None, Mo.nu, Mo.ne, Mo.me, Mo.le, n, n, l, k, L=1.8 * n * h, Lp=4.0 * n * h)
+    assert _rel(Mgen * b, y_ref) <= TOL
+    if n == 48:
+        # rhs and the unpreconditioned GMRES of example3D.jl:71-78 against the oracle history
+        from oracle.gmres_is import gmres as gmres_oracle
+        X, Y, Z = O.grid3d(x, x, z)
+        u_inc = np.exp(1j * k * X)
+        rhs = -(Mo * u_inc - u_inc)
+        xo, hist_o, _, _ = gmres_oracle(np.zeros(N, complex), lambda v: Mo * v, rhs, maxiter=25)
+        xg, hg = ls.gmres_(np.zeros(N, complex), Mg, rhs, maxiter=25, log=True)
+        assert hg.iters == len(hist_o)
+        assert np.max(np.abs(hg["resnorm"] - hist_o) / hist_o) < 1e-8
