@@ -237,3 +237,51 @@ def test_gmres_other_orthogonalisations(orth):
     assert np.abs(hcol[:11] - href).max() < 1e-12 * np.abs(href).max()
     assert abs(hcol[11] - np.linalg.norm(wr)) < 1e-12 * np.linalg.norm(wr)
     assert _rel(dw.to_host(), wr / np.linalg.norm(wr)) < 1e-12
+
+
+def test_gmres_options_and_error_paths():
+    """initially_zero, abstol, restart bounds, a failing Msp callback, two operators alive at once."""
+    from oracle import ls_oracle as O
+    from oracle.gmres_is import gmres as gmres_oracle
+    import fast_solver_lippmann_schwinger_b200 as ls
+    n = 64
+    x, h, k, Mo = O.pow2_problem_2d(n)
+    N = n * n
+    A1 = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, n, n, k, quadRule="Greengard_Vico")
+    A2 = ls.FastM(Mo.GFFT, 2.0 * Mo.nu, Mo.ne, Mo.me, n, n, k, quadRule="Greengard_Vico")     # a second handle, own stream
+    rng = np.random.default_rng(17)
+    rhs = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    # initially_zero skips the first mul! (mv_products starts at 1 upstream)
+    xo, ho, co, mvo = gmres_oracle(np.zeros(N, complex), lambda v: O.fastconvolution(Mo, v), rhs, maxiter=15, initially_zero=True)
+    xg, hg = ls.gmres_(np.zeros(N, complex), A1, rhs, maxiter=15, log=True, initially_zero=True)
+    assert hg.mvps == mvo and hg.iters == len(ho)
+    assert np.max(np.abs(hg["resnorm"] - ho) / ho) < 1e-8
+    # abstol stops early; restart = 64 is the largest basis served
+    xg, hg = ls.gmres_(np.zeros(N, complex), A1, rhs, abstol=1e30, log=True)
+    assert hg.iters == 0 and hg.isconverged
+    xg, hg64 = ls.gmres_(np.zeros(N, complex), A1, rhs, restart=64, maxiter=70, reltol=1e-12, log=True)
+    xo, ho64, _, _ = gmres_oracle(np.zeros(N, complex), lambda v: O.fastconvolution(Mo, v), rhs, restart=64, maxiter=70, reltol=1e-12)
+    assert hg64.iters == len(ho64)
+    sig = ho64 > 1e-8 * ho64[0]          # below ~1e-8 of the start the estimate is dominated by rounding in both codes
+    assert np.max(np.abs(hg64["resnorm"][sig] - ho64[sig]) / ho64[sig]) < 1e-8
+    with pytest.raises(ls.LSUnsupported):
+        ls.gmres_(np.zeros(N, complex), A1, rhs, restart=65, maxiter=3)
+    # interleaved applies on two handles give independent, correct results
+    b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    y1, y2 = A1 * b, A2 * b
+    assert _rel(y1, O.fastconvolution(Mo, b)) < 1e-12
+    assert _rel((y2 - b), 2.0 * (y1 - b)) < 1e-12
+    # a preconditioner whose host solve fails must surface as an error, not a wrong answer
+    import scipy.sparse as sp
+    P = ls.SparsifyingPreconditioner(sp.identity(N, dtype=complex, format="csc"), sp.identity(N, dtype=complex, format="csc"))
+
+    class Boom:
+        def solve(self, v):
+            raise RuntimeError("factorisation lost")
+    P.MspInv = Boom()
+    with pytest.raises(ls.LSCudaError) as ei:
+        ls.gmres_(np.zeros(N, complex), A1, rhs, Pl=P, maxiter=3)
+    assert ei.value.code == -6
+    # wrong-size vectors are DimensionMismatch-like errors on the host side
+    with pytest.raises(ValueError):
+        ls.gmres_(np.zeros(N - 1, complex), A1, rhs, maxiter=3)
