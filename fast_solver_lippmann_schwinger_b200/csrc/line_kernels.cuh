@@ -271,6 +271,81 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     for (int a = AR; a < E; ++a) o[(long)(a * T) * la.out_es] = accs[(a - AR) * TH];
 }
 
+// ---- middle, fused, lean variant for short strided lines (mode B, 3-D z pass) ------------------------------
+// Same arithmetic as k_mid_fused with the spectrum staged by TMA.  The input line group is not copied to
+// shared memory: in mode B a line group is read as 128-byte segments, so re-reading it for each of the four
+// sub-transforms (L2 hits after the first) is cheap, and without the copy a CTA needs 64 KB + tables instead
+// of 96 KB - three CTAs per SM when the registers allow (MINB).
+// smem: [exchange: LPC*N][spectrum chunk: LPC*N][tw1][mbarrier]
+template <int N, int MINB>
+__global__ void __launch_bounds__(GeoB<N>::THREADS, MINB)
+k_mid_lean(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB, const LineAddr la, long line0) {
+    typedef Map<N, true> M;
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
+    constexpr int UNIT = 8 * N, UPC = LPC * N / UNIT;
+    extern __shared__ __align__(128) cd sm[];
+    M mp;
+    cd* ex = sm + sm_group_off(mp);
+    cd* gb = sm + LPC * N;
+    cd* tw1 = sm + 2 * LPC * N;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tw1 + EngTab<N>::TW1N);
+    const long Lcta = line0 + (long)blockIdx.x * LPC;
+    const long L = Lcta + mp.line;
+    const int t = mp.t;
+    const cd* gsrc = G + (Lcta >> 3) * 4L * UNIT;
+    auto issue_g = [&](int r) {
+        mbar_expect_tx(bar, (unsigned)(UPC * UNIT * sizeof(cd)));
+#pragma unroll
+        for (int u = 0; u < UPC; ++u)
+            bulk_g2s(gb + u * UNIT, gsrc + ((long)u * 4 + r) * UNIT, (unsigned)(UNIT * sizeof(cd)), bar);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_proxy_async();
+        issue_g(0);
+    }
+    load_tw1<N>(tw1, TAB);
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    const cd* p = in + line_in(la, L) + (long)t * la.in_es;
+    __syncthreads();
+    cd acc[E];
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        cd v[E];
+#pragma unroll
+        for (int a = 0; a < E; ++a) v[a] = p[(long)(a * T) * la.in_es];
+        fft_fwd<N>(v, t, r, ex, mp.lay, tw);
+        mbar_wait(bar, (unsigned)(r & 1));
+        const cd* g = gb + sm_group_off(mp);
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cmul(v[e], g[(t + T * e) * 8 + mp.lay_lam()]);
+        fft_inv<N>(v, t, r, ex, mp.lay, tw, [&]() {
+            if (r < 3 && threadIdx.x == 0) {
+                fence_proxy_async();
+                issue_g(r + 1);
+            }
+        });
+        demod_accumulate<N>(acc, v, r);
+    }
+    cd* o = out + line_out(la, L) + (long)t * la.out_es;
+#pragma unroll
+    for (int a = 0; a < E; ++a) o[(long)(a * T) * la.out_es] = acc[a];
+}
+
+template <int N, int MINB>
+inline cudaError_t launch_mid_lean(cudaStream_t s, long nlines, const cd* in, cd* out, const cd* G, const cd* TAB,
+                                   const LineAddr& la) {
+    constexpr int smem = (2 * GeoB<N>::LPC * N + EngTab<N>::TW1N) * (int)sizeof(cd) + 16;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_mid_lean<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    k_mid_lean<N, MINB><<<(unsigned)(nlines / GeoB<N>::LPC), GeoB<N>::THREADS, smem, s>>>(in, out, G, TAB, la, 0);
+    return cudaPeekAtLastError();
+}
+
 // ---- middle, fused, persistent CTAs with an asynchronously prefetched input line (mode A) -------------
 // Same arithmetic as k_mid_fused (spectrum straight from HBM, requested before the last butterfly stage).
 // A CTA walks over line groups with stride gridDim.x; while it transforms one group, the next group's

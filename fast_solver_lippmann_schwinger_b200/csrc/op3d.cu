@@ -154,7 +154,10 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
         if (variant < 0) { const char* ev = getenv("LS_P3_VARIANT"); variant = ev ? atoi(ev) : 1; }   // 1: spectrum chunks staged by TMA bulk copies (5.96 ms at 256^3), 0: direct loads (7.1 ms)
 #define C3(N) launch_mid<N, true, false>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
 #define C3T(N) launch_mid<N, true, true>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
-        if (variant == 1) { LS3_DISPATCH(l, C3T); } else { LS3_DISPATCH(l, C3); }
+#define C3L2(N) launch_mid_lean<N, 2>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
+#define C3L3(N) launch_mid_lean<N, (GeoB<N>::THREADS <= 128 ? 3 : 1)>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
+        if (variant == 1) { LS3_DISPATCH(l, C3T); } else if (variant == 2) { LS3_DISPATCH(l, C3L2); }
+        else if (variant == 3) { LS3_DISPATCH(l, C3L3); } else { LS3_DISPATCH(l, C3); }
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
