@@ -308,6 +308,19 @@ __device__ __forceinline__ void demod_accumulate(cd* acc, const cd* v, int r) {
     }
 }
 
+// same for an output block other than the first: every term carries the extra factor conj(w_64^shift)
+template <int N>
+__device__ __forceinline__ void demod_accumulate_block(cd* acc, const cd* v, int r, int shift) {
+    constexpr int E = Cfg<N>::E;
+    if (r == 0) {
+#pragma unroll
+        for (int a = 0; a < E; ++a) acc[a] = v[a];
+    } else {
+#pragma unroll
+        for (int a = 0; a < E; ++a) acc[a] = cfmac(v[a], c64(r * a * (16 / E) + shift), acc[a]);
+    }
+}
+
 // middle / last stages ------------------------------------------------------------------
 template <int N, int I>
 __device__ __forceinline__ void fwd_stage(cd* v, int t, const TwState<N>& tw) {

@@ -76,6 +76,11 @@ struct LineAddr {
     // (s & (2^shift - 1))*es + (s >> shift)*split_stride.  shift = 62 disables it.
     int split_shift = 62;
     long split_stride = 0;
+    // padding factor of the line: nr = 4 sub-transforms r = 0..3 (the reference's 4N zero padding) or
+    // nr = 2 (r = 0, 2 in units of w_4N: a 2N padding, enough once the kernel is restricted to lags (-N, N))
+    int nr = 4;
+    int cblock = 0;     // inverse: which N-block [cblock*N, (cblock+1)*N) of the padded output line is kept
+    int full2 = 0;      // forward: the input line has 2N points (no zero padding), nr must be 2
 };
 __device__ __forceinline__ long slot_off(const LineAddr& a, long s, long es) {
     return (s & ((1L << a.split_shift) - 1)) * es + (s >> a.split_shift) * a.split_stride;
@@ -125,15 +130,26 @@ k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __res
         x[a] = val;
     }
     __syncthreads();   // tw1 visible
+    const int nr = la.nr, rstep = 4 / la.nr;
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
+    for (int rr = 0; rr < nr; ++rr) {
+        const int r = rr * rstep;
         cd v[E];
+        if (la.full2) {
+            // unpadded 2N-point line (setup only): first DIF stage x[j] +- x[j + N]
 #pragma unroll
-        for (int a = 0; a < E; ++a) v[a] = x[a];
+            for (int a = 0; a < E; ++a) {
+                const cd hi = in[in_base + (long)(N + a * T + t) * in_es];
+                v[a] = rr == 0 ? cadd(x[a], hi) : csub(x[a], hi);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < E; ++a) v[a] = x[a];
+        }
         fft_fwd<N>(v, t, r, ex, mp.lay, tw);
         cd* o = out + out_base;
 #pragma unroll
-        for (int e = 0; e < E; ++e) o[slot_off(la, (long)(r * N + t + T * e), out_es)] = v[e];
+        for (int e = 0; e < E; ++e) o[slot_off(la, (long)(rr * N + t + T * e), out_es)] = v[e];
         __syncthreads();   // next forward rewrites the exchange buffer at other addresses
     }
 }
@@ -167,13 +183,14 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     const long Lcta = line0 + (long)blockIdx.x * LPC;
     const long L = Lcta + mp.line;
     const int t = mp.t;
-    const cd* gsrc = G + (MODE_B ? (Lcta >> 3) : Lcta) * 4L * UNIT;   // chunk (unit u, r) at gsrc + (u*4 + r)*UNIT
+    const int nr = la.nr, rstep = 4 / la.nr;
+    const cd* gsrc = G + (MODE_B ? (Lcta >> 3) : Lcta) * (long)nr * UNIT;   // chunk (unit u, rr) at gsrc + (u*nr + rr)*UNIT
 
-    auto issue_g = [&](int r) {
+    auto issue_g = [&](int rr) {
         mbar_expect_tx(bar, (unsigned)(UPC * UNIT * sizeof(cd)));
 #pragma unroll
         for (int u = 0; u < UPC; ++u)
-            bulk_g2s(gb + u * UNIT, gsrc + ((long)u * 4 + r) * UNIT, (unsigned)(UNIT * sizeof(cd)), bar);
+            bulk_g2s(gb + u * UNIT, gsrc + ((long)u * nr + rr) * UNIT, (unsigned)(UNIT * sizeof(cd)), bar);
     };
     if (GSM && threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -188,10 +205,10 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
         for (int a = 0; a < E; ++a) xs[mp.lay.phys(a * T + t)] = p[(long)(a * T) * la.in_es];
     }
     // direct-load variant: pull spectrum chunk r into L2 one r ahead (one request per 128-byte line)
-    auto prefetch_g = [&](int r) {
-        if (!GSM && r < 4) {
-            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * 4 + r) * UNIT + mp.lay_lam()
-                                 : gsrc + ((long)mp.line * 4 + r) * UNIT;
+    auto prefetch_g = [&](int rr) {
+        if (!GSM && rr < nr) {
+            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * nr + rr) * UNIT + mp.lay_lam()
+                                 : gsrc + ((long)mp.line * nr + rr) * UNIT;
             constexpr int gs = MODE_B ? 8 : 1;
             if (MODE_B ? (mp.lay_lam() == 0) : ((t & 7) == 0)) {
 #pragma unroll
@@ -204,16 +221,17 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     cd acc[AR];
     const int goff = MODE_B ? 0 : mp.line * N;     // mode B: lay.phys already interleaves the 8 lines
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
+    for (int rr = 0; rr < nr; ++rr) {
+        const int r = rr * rstep;
         cd v[E];
 #pragma unroll
         for (int a = 0; a < E; ++a) v[a] = xs[mp.lay.phys(a * T + t)];
-        prefetch_g(r + 1);
+        prefetch_g(rr + 1);
         if (!GSM && MINB >= 3) {
             // three CTAs per SM: registers are the scarce resource, the other CTAs hide the load latency
             fft_fwd<N>(v, t, r, ex, mp.lay, tw);
-            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * 4 + r) * UNIT + mp.lay_lam()
-                                 : gsrc + ((long)mp.line * 4 + r) * UNIT;
+            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * nr + rr) * UNIT + mp.lay_lam()
+                                 : gsrc + ((long)mp.line * nr + rr) * UNIT;
             constexpr int gs = MODE_B ? 8 : 1;
 #pragma unroll
             for (int e = 0; e < E; ++e) v[e] = cmul(v[e], __ldg(&g[(t + T * e) * gs]));
@@ -221,8 +239,8 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
             // spectrum values are requested before the last butterfly stage and consumed after it
             cd gv[E];
             fft_fwd<N>(v, t, r, ex, mp.lay, tw, [&]() {
-                const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * 4 + r) * UNIT + mp.lay_lam()
-                                     : gsrc + ((long)mp.line * 4 + r) * UNIT;
+                const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * nr + rr) * UNIT + mp.lay_lam()
+                                     : gsrc + ((long)mp.line * nr + rr) * UNIT;
                 constexpr int gs = MODE_B ? 8 : 1;
 #pragma unroll
                 for (int e = 0; e < E; ++e) gv[e] = __ldg(&g[(t + T * e) * gs]);
@@ -231,7 +249,7 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
             for (int e = 0; e < E; ++e) v[e] = cmul(v[e], gv[e]);
         } else {
         fft_fwd<N>(v, t, r, ex, mp.lay, tw);
-        mbar_wait(bar, (unsigned)(r & 1));
+        mbar_wait(bar, (unsigned)(rr & 1));
         if (MODE_B) {
             const cd* g = gb + sm_group_off(mp);
 #pragma unroll
@@ -244,9 +262,9 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
         }
         fft_inv<N>(v, t, r, ex, mp.lay, tw, [&]() {
             // every thread has consumed gb (the multiply precedes this barrier): refill it
-            if (GSM && r < 3 && threadIdx.x == 0) {
+            if (GSM && rr + 1 < nr && threadIdx.x == 0) {
                 fence_proxy_async();
-                issue_g(r + 1);
+                issue_g(rr + 1);
             }
         });
         if (ASM == 0) {
@@ -626,27 +644,30 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __res
     __syncthreads();
     const long in_base = line_in(la, L), out_base = line_out(la, L);
     cd acc[E];
+    const int nr = la.nr, rstep = 4 / la.nr;
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
+    for (int rr = 0; rr < nr; ++rr) {
+        const int r = rr * rstep;
         cd v[E];
         const cd* p = in + in_base;
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = p[slot_off(la, (long)(r * N + t + T * e), la.in_es)];
+        for (int e = 0; e < E; ++e) v[e] = p[slot_off(la, (long)(rr * N + t + T * e), la.in_es)];
         // pull the next block (or, at the end, the b values of the combine) into L2 while this one is transformed
         // (contiguous lines only: measured on B200, prefetching scattered 16-byte pieces costs more L2
         //  requests than the latency it hides - 2-D P3 0.177 -> 0.223 ms, 3-D P5 0.54 -> 0.44 ms)
         if (!PF) {
-        } else if (r < 3) {
+        } else if (rr + 1 < nr) {
             if (!MODE_B && la.in_es == 1 && (t & 7) == 0) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) prefetch_l2(&p[slot_off(la, (long)((r + 1) * N + t + T * e), 1)]);
+                for (int e = 0; e < E; ++e) prefetch_l2(&p[slot_off(la, (long)((rr + 1) * N + t + T * e), 1)]);
             }
         } else if (bsrc != nullptr && !MODE_B && la.in_es == 1 && (t & 7) == 0) {
 #pragma unroll
             for (int a = 0; a < E; ++a) prefetch_l2(&bsrc[out_base + (long)(a * T + t) * la.out_es]);
         }
         fft_inv<N>(v, t, r, ex, mp.lay, tw);
-        demod_accumulate<N>(acc, v, r);
+        if (la.cblock == 0) demod_accumulate<N>(acc, v, r);
+        else demod_accumulate_block<N>(acc, v, r, 16 * r * la.cblock);     // kept block c: extra factor w_4^(-r c)
         __syncthreads();
     }
 #pragma unroll

@@ -4,7 +4,16 @@
 //   P1  k_fwd_pruned  columns (x, contiguous):  b, nu      -> A  [ne x m]   (slot order in x)
 //   P2  k_mid_fused   rows (y): A, Green spectrum          -> C  [m x ne]   (line contiguous)
 //   P3  k_inv_pruned  columns (x): C, b                    -> y
-// Algorithmic HBM bytes per apply: 568*N  (SURVEY.md section 8(d)).
+// Padding.  The reference pads 4x per dimension (Greengard_Vico) because the truncated-kernel spectrum has
+// to be *built* on the 4n grid; the apply itself only ever touches the spatial kernel g = ifft2(GFFT) at the
+// lags (-n, n) x (-m, m) (input supported on [0,n), output cropped to [0,n)).  At create time the handle
+// therefore computes g on the device (pruned inverse transforms of the given GFFT), wraps those lags onto a
+// 2n x 2m grid and transforms back: G2 = fft2(g2).  Every apply then runs with 2x padding - the same linear
+// operator to rounding (measured 1e-16 relative against the literal 4x evaluation), a quarter of the
+// spectrum, half of the intermediates and about a third of the FP64 work.  LS_FLAG_PAD4 keeps the literal
+// 4x evaluation (tests compare the two).
+// Algorithmic HBM bytes per apply: 2x padding 24N + 64N + 64N + 64N + 32N = 248*N;
+//                                  4x padding 568*N.
 #include "ls_common.cuh"
 #include "op2d_base.cuh"
 #include "line_kernels.cuh"
@@ -15,13 +24,22 @@ using namespace lsk;
 namespace {
 
 struct Op2D : Op2DBase {
+    int nr = 4;               // padding factor actually used by the applies (4: literal, 2: compact)
+    long pn = 0, pm = 0;      // padded sizes nr*n, nr*m
     double* d_nu = nullptr;
-    cd* d_G = nullptr;        // [sx][ry][slot_y], scaled by 1/(ne*me)
+    cd* d_G = nullptr;        // [sx][ry][slot_y] on the pn x pm grid, normalisation folded in
     cd* d_TABn = nullptr; cd* d_TABm = nullptr;   // engine tables (fft_engine.cuh EngTab)
-    cd* d_A = nullptr;        // ne x m
-    cd* d_C = nullptr;        // m x ne (line contiguous)
+    cd* d_A = nullptr;        // pn x m
+    cd* d_C = nullptr;        // m x pn (line contiguous)
     int apply_dev(const cd* b, cd* y, int mode) override;
 };
+
+__global__ void k_scale(cd* a, long n, double s) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        cd v = a[i];
+        a[i] = make_double2(v.x * s, v.y * s);
+    }
+}
 
 // Gd[(sx*4 + ry)*m + sy] = GFFT[(4 fx[sx%n] + sx/n + ne/2) % ne, (4 fy[sy] + ry + me/2) % me] / (ne*me)
 __global__ void k_permute_g2d(const cd* __restrict__ gin, cd* __restrict__ gout,
@@ -48,9 +66,10 @@ template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
         attr = true;
     }
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
+    LineAddr la{1L << 40, op->n, 0, 1, op->pn, 0, 1};
+    la.nr = op->nr;
     op->phase_begin(0);
-    k_fwd_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        b, nu, op->d_A, op->d_TABn, LineAddr{1L << 40, op->n, 0, 1, op->ne, 0, 1}, 0);
+    k_fwd_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(b, nu, op->d_A, op->d_TABn, la, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
@@ -65,11 +84,13 @@ template <int N, bool GSM, int MINB, int ASM = 0> int launch_mid_v(Op2D* op) {
         LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false, GSM, MINB, ASM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    dim3 grid((unsigned)(op->ne / GeoA<N>::LPC));
-    // line = x slot sx; point j at A[sx + ne*j]; output line contiguous C[j + m*sx]
+    dim3 grid((unsigned)(op->pn / GeoA<N>::LPC));
+    // line = x slot sx; point j at A[sx + pn*j]; output line contiguous C[j + m*sx]
+    LineAddr la{1L << 40, 1, 0, op->pn, op->m, 0, 1};
+    la.nr = op->nr;
     op->phase_begin(1);
     k_mid_fused<N, false, GSM, MINB, ASM><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        op->d_A, op->d_C, op->d_G, op->d_TABm, LineAddr{1L << 40, 1, 0, op->ne, op->m, 0, 1}, 0);
+        op->d_A, op->d_C, op->d_G, op->d_TABm, la, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
@@ -91,6 +112,7 @@ template <int N, int ASM> int launch_mid_dual(Op2D* op) {
 }
 template <int N> int launch_mid(Op2D* op) {
     static int variant = -1;
+    if (op->nr != 4) return launch_mid_v<N, false, 1>(op);      // the experiment kernels below are 4x-padding only
     // variants measured on B200 at 2048^2 (profiles/r1_b_notes.md): 1 = spectrum straight from HBM into
     // registers (0.706 ms), 0 = spectrum staged in shared memory by TMA bulk copies (0.761 ms)
     if (variant < 0) { const char* e = getenv("LS_P2_VARIANT"); variant = e ? atoi(e) : 1; }
@@ -136,9 +158,10 @@ template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
     }
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
     // line = column j; slot sx at C[j + m*sx]
+    LineAddr la{1L << 40, 1, 0, op->m, op->n, 0, 1};
+    la.nr = op->nr;
     op->phase_begin(2);
-    k_inv_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
-        op->d_C, bsrc, y, op->d_TABn, scale, LineAddr{1L << 40, 1, 0, op->m, op->n, 0, 1}, 0);
+    k_inv_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(op->d_C, bsrc, y, op->d_TABn, scale, la, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
@@ -177,6 +200,80 @@ int apply_device(Op2D* op, const cd* b, cd* y, int mode) {
 }  // namespace
 
 int Op2D::apply_dev(const cd* b, cd* y, int mode) { return apply_device(this, b, y, mode); }
+
+namespace {
+
+#define LS_DISPATCH_E(N_, CALL)                                                    \
+    switch (N_) {                                                                  \
+        case 64:   e = CALL(64); break;                                            \
+        case 128:  e = CALL(128); break;                                           \
+        case 256:  e = CALL(256); break;                                           \
+        case 512:  e = CALL(512); break;                                           \
+        case 1024: e = CALL(1024); break;                                          \
+        case 2048: e = CALL(2048); break;                                          \
+        case 4096: e = CALL(4096); break;                                          \
+        default: e = cudaErrorInvalidValue;                                        \
+    }
+
+// Compact (2x) spectrum from the reference's 4x one.  g4s: [sx4][ry][sy] slot order on the 4n x 4m grid,
+// already scaled by 1/(ne me).  On return op->d_G holds G2 = fft2(g wrapped onto 2n x 2m) in the slot order
+// of the nr = 2 kernels, scaled by 1/(2n 2m).
+int compact_spectrum(Op2D* op, cd* g4s) {
+    const long n = op->n, m = op->m;
+    cudaStream_t s = op->stream;
+    cudaError_t e = cudaSuccess;
+    cd *t1 = nullptr, *g2 = nullptr, *t2 = nullptr, *G2 = nullptr;
+    int rc;
+    if ((rc = op->dmalloc((void**)&t1, (size_t)(4 * n) * (2 * m) * sizeof(cd)))) return rc;
+    // (1) inverse along y, keep lags [0, m) and [-m, 0): T1[sx4*2m + jy2]
+    for (int c = 0; c <= 3; c += 3) {
+        LineAddr la{1L << 40, 4 * m, 0, 1, 2 * m, 0, 1};
+        la.nr = 4; la.cblock = c;
+        cd* outp = t1 + (c ? m : 0);
+#define S1(N) launch_inv<N, false>(s, 4 * n, g4s, nullptr, outp, op->d_TABm, 1.0, la)
+        LS_DISPATCH_E(m, S1);
+        LS_CUDA_TRY(e);
+    }
+    LS_CUDA_TRY(cudaStreamSynchronize(s));
+    op->dfree(g4s);
+    if ((rc = op->dmalloc((void**)&g2, (size_t)(2 * n) * (2 * m) * sizeof(cd)))) return rc;
+    // (2) inverse along x: g2[jx2 + 2n*jy2]
+    for (int c = 0; c <= 3; c += 3) {
+        LineAddr la{1L << 40, 1, 0, 2 * m, 2 * n, 0, 1};
+        la.nr = 4; la.cblock = c;
+        cd* outp = g2 + (c ? n : 0);
+#define S2(N) launch_inv<N, false>(s, 2 * m, t1, nullptr, outp, op->d_TABn, 1.0, la)
+        LS_DISPATCH_E(n, S2);
+        LS_CUDA_TRY(e);
+    }
+    LS_CUDA_TRY(cudaStreamSynchronize(s));
+    op->dfree(t1);
+    if ((rc = op->dmalloc((void**)&t2, (size_t)(2 * n) * (2 * m) * sizeof(cd)))) return rc;
+    if ((rc = op->dmalloc((void**)&G2, (size_t)(2 * n) * (2 * m) * sizeof(cd)))) return rc;
+    {   // (3) forward along x on the full 2n-point lines: T2[sx2 + 2n*jy2]
+        LineAddr la{1L << 40, 2 * n, 0, 1, 2 * n, 0, 1};
+        la.nr = 2; la.full2 = 1;
+#define S3(N) launch_fwd<N, false>(s, 2 * m, g2, nullptr, t2, op->d_TABn, la)
+        LS_DISPATCH_E(n, S3);
+        LS_CUDA_TRY(e);
+    }
+    {   // (4) forward along y: G2[sx2*2m + (ry*m + sy)]
+        LineAddr la{1L << 40, 1, 0, 2 * n, 2 * m, 0, 1};
+        la.nr = 2; la.full2 = 1;
+#define S4(N) launch_fwd<N, false>(s, 2 * n, t2, nullptr, G2, op->d_TABm, la)
+        LS_DISPATCH_E(m, S4);
+        LS_CUDA_TRY(e);
+    }
+    k_scale<<<148 * 8, 256, 0, s>>>(G2, (2 * n) * (2 * m), 1.0 / ((double)(2 * n) * (double)(2 * m)));
+    LS_CUDA_TRY(cudaStreamSynchronize(s));
+    op->dfree(g2);
+    op->dfree(t2);
+    op->d_G = G2;
+    op->nr = 2;
+    return LS_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -224,8 +321,15 @@ int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
         if (e != cudaSuccess) { set_error("spectrum permutation failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
         op->dfree(d_gin); op->dfree(d_fx); op->dfree(d_fy);
     }
-    TRY(op->dmalloc((void**)&op->d_A, (size_t)ne * m * sizeof(cd)));
-    TRY(op->dmalloc((void**)&op->d_C, (size_t)ne * m * sizeof(cd)));
+    op->nr = 4;
+    if (!(flags & LS_FLAG_PAD4)) {
+        cd* g4s = op->d_G;
+        op->d_G = nullptr;
+        TRY(compact_spectrum(op, g4s));
+    }
+    op->pn = op->nr * n; op->pm = op->nr * m;
+    TRY(op->dmalloc((void**)&op->d_A, (size_t)op->pn * m * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_C, (size_t)op->pn * m * sizeof(cd)));
     TRY(op->dmalloc((void**)&op->d_b, N * sizeof(cd)));
     TRY(op->dmalloc((void**)&op->d_y, N * sizeof(cd)));
 #undef TRY

@@ -94,7 +94,7 @@ class FastM(_Handle):
     into a one-time device permutation).
     """
 
-    def __init__(self, GFFT, nu, ne, me, n, m, k, quadRule="trapezoidal", force_generic=False):
+    def __init__(self, GFFT, nu, ne, me, n, m, k, quadRule="trapezoidal", force_generic=False, pad4=False):
         super().__init__()
         self.ne, self.me, self.n, self.m = int(ne), int(me), int(n), int(m)
         self.omega = float(k)
@@ -111,7 +111,7 @@ class FastM(_Handle):
         g = np.asfortranarray(GFFT.astype(np.complex128, copy=False))   # column-major, as Julia stores it
         check(lib().ls_op2d_create(C.byref(self._h), self.n, self.m, self.ne, self.me, ptr(nu),
                                    C.c_void_p(g.ctypes.data), self.omega, _lib.QUADRULES[quadRule],
-                                   1 if force_generic else 0))
+                                   (1 if force_generic else 0) | (2 if pad4 else 0)))
 
     # size / eltype, FastConvolution.jl:31-41 (Q1: size(M) is a tuple of tuples upstream)
     def size(self, dim=None):

@@ -39,6 +39,9 @@ typedef struct ls_handle_s* ls_handle;
 
 /* create flags */
 #define LS_FLAG_FORCE_GENERIC 1   /* take the general-size (Bluestein) path even for power-of-two grids (tests) */
+#define LS_FLAG_PAD4          2   /* evaluate with the reference's literal 4x zero padding; default: the handle restricts
+                                     the kernel to the lags the cropped apply touches and runs with 2x padding (same
+                                     operator to rounding, see csrc/op2d.cu) */
 
 #define LS_MEM_HOST   0
 #define LS_MEM_DEVICE 1

@@ -96,3 +96,26 @@ def test_unsupported_and_invalid_inputs():
         M._apply(np.zeros(64 * 64, complex), None, 7)                  # unknown mode
     with pytest.raises(ValueError):
         ls.FastM(np.zeros((256, 255), complex), np.zeros(64 * 64), 256, 256, 64, 64, 1.0, quadRule="Greengard_Vico")
+
+
+@pytest.mark.parametrize("n,m", [(128, 128), (64, 256), (512, 512)])
+def test_compact_padding_equals_literal_4x(n, m):
+    """Default handles restrict the kernel to the lags the cropped apply touches and run with 2x padding;
+    pad4=True evaluates the reference's literal 4x zero padding.  Same operator to rounding."""
+    from oracle import ls_oracle as O
+    import fast_solver_lippmann_schwinger_b200 as ls
+    Mo = _problem(n, m)
+    A2 = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, n, m, Mo.omega, quadRule="Greengard_Vico")
+    A4 = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, n, m, Mo.omega, quadRule="Greengard_Vico", pad4=True)
+    rng = np.random.default_rng(n + m)
+    b = rng.standard_normal(n * m) + 1j * rng.standard_normal(n * m)
+    y2, y4 = A2 * b, A4 * b
+    ref = O.fastconvolution(Mo, b)
+    assert _rel(y2, ref) <= TOL and _rel(y4, ref) <= TOL
+    assert _rel(y2 - b, y4 - b) <= 1e-12          # the convolution part alone
+    # a spectrum that is NOT mirror symmetric (random): the restriction argument does not need symmetry
+    G = (rng.standard_normal((4 * n, 4 * m)) + 1j * rng.standard_normal((4 * n, 4 * m))) / (n * m)
+    nu = rng.standard_normal(n * m)
+    B2 = ls.FastM(G, nu, 4 * n, 4 * m, n, m, 1.3, quadRule="Greengard_Vico")
+    Bo = O.FastM(G, nu, 4 * n, 4 * m, n, m, 1.3, quadRule="Greengard_Vico")
+    assert _rel(B2 * b, O.fastconvolution(Bo, b)) <= TOL
