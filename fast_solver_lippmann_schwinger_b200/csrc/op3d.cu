@@ -27,8 +27,10 @@ namespace {
 
 struct Op3D : HandleBase {
     long n = 0, m = 0, l = 0, ne = 0, me = 0, le = 0;
+    int nr = 4;                        // padding factor used by the applies (4: literal, 2: compact - see op2d.cu)
+    long pn = 0, pm = 0, pl = 0;       // padded sizes nr*n, nr*m, nr*l
     int P = 1, rank = 0;
-    long nel = 0, lloc = 0;            // x-slots / z-planes owned by this rank
+    long nel = 0, lloc = 0;            // x-slots (pn/P) / z-planes (l/P) owned by this rank
     ncclComm_t comm = nullptr;
     double omega = 0;
     double* d_nu = nullptr;            // local z slab
@@ -113,7 +115,8 @@ int all_to_all(Op3D* op, const cd* send, cd* recv, long blk_elems) {
 int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     cudaError_t e = cudaSuccess;
     cudaStream_t s = op->stream;
-    const long n = op->n, m = op->m, l = op->l, me = op->me, nel = op->nel, lloc = op->lloc;
+    const long n = op->n, m = op->m, l = op->l, me = op->pm, nel = op->nel, lloc = op->lloc;
+    const int nr = op->nr;
     const bool full = (mode == LS_APPLY_FASTCONVOLUTION);
     const long blk = nel * m * lloc;                 // elements exchanged with each peer
     int shift = 0;
@@ -121,7 +124,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     // P1: x lines (j, p_loc): in b[n*line + i]; slot sx -> block sx/nel, A1[(sx/nel)*blk + nel*line + sx%nel]
     {
         LineAddr la{1L << 40, n, 0, 1, nel, 0, 1};
-        la.split_shift = shift; la.split_stride = blk;
+        la.split_shift = shift; la.split_stride = blk; la.nr = nr;
         op->phase_begin(0);
 #define C1(N) launch_fwd<N, false>(s, m * lloc, b, full ? op->d_nu : nullptr, op->d_A1, op->d_TABn, la)
         LS3_DISPATCH(n, C1);
@@ -140,6 +143,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     // P2: y lines (sxl, p): in A1T[sxl + nel*m*p + nel*j]; out A2[sxl + nel*me*p + nel*sy]
     {
         LineAddr la{nel, 1, nel * m, nel, 1, nel * me, nel};
+        la.nr = nr;
         op->phase_begin(1);
 #define C2(N) launch_fwd<N, true>(s, nel * l, a1t, nullptr, op->d_A2, op->d_TABm, la)
         LS3_DISPATCH(m, C2);
@@ -149,6 +153,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     // P3: z lines L = sxl + nel*sy: point p at A2[L + nel*me*p], in place
     {
         LineAddr la{1L << 40, 1, 0, nel * me, 1, 0, nel * me};
+        la.nr = nr;
         op->phase_begin(2);
         static int variant = -1;
         if (variant < 0) { const char* ev = getenv("LS_P3_VARIANT"); variant = ev ? atoi(ev) : 1; }   // 1: spectrum chunks staged by TMA bulk copies (5.96 ms at 256^3), 0: direct loads (7.1 ms)
@@ -156,7 +161,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
 #define C3T(N) launch_mid<N, true, true>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
 #define C3L2(N) launch_mid_lean<N, 2>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
 #define C3L3(N) launch_mid_lean<N, (GeoB<N>::THREADS <= 128 ? 3 : 1)>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
-        if (variant == 1) { LS3_DISPATCH(l, C3T); } else if (variant == 2) { LS3_DISPATCH(l, C3L2); }
+        if (variant == 1 || nr != 4) { LS3_DISPATCH(l, C3T); } else if (variant == 2) { LS3_DISPATCH(l, C3L2); }
         else if (variant == 3) { LS3_DISPATCH(l, C3L3); } else { LS3_DISPATCH(l, C3); }
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
@@ -164,6 +169,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     // P4: inverse y lines (sxl, p): slots at A2[sxl + nel*me*p + nel*sy]; out C1T[sxl + nel*m*p + nel*j]
     {
         LineAddr la{nel, 1, nel * me, nel, 1, nel * m, nel};
+        la.nr = nr;
         op->phase_begin(3);
 #define C4(N) launch_inv<N, true>(s, nel * l, op->d_A2, nullptr, c1t, op->d_TABm, 1.0, la)
         LS3_DISPATCH(m, C4);
@@ -179,7 +185,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     // P5: inverse x lines + combine; slot sx of line (j, p_loc) at A1[(sx/nel)*blk + nel*line + sx%nel]
     {
         LineAddr la{1L << 40, nel, 0, 1, n, 0, 1};
-        la.split_shift = shift; la.split_stride = blk;
+        la.split_shift = shift; la.split_stride = blk; la.nr = nr;
         op->phase_begin(4);
 #define C5(N) launch_inv<N, false, true>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
         LS3_DISPATCH(n, C5);
@@ -189,9 +195,97 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     return LS_OK;
 }
 
+__global__ void k_scale3(cd* a, long n, double s) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        cd v = a[i];
+        a[i] = make_double2(v.x * s, v.y * s);
+    }
+}
+
+// Compact (2x) spectrum, 3-D version of compact_spectrum() in op2d.cu: the kernel g = ifftn(GFFT) is only
+// needed at the lags (-n,n) x (-m,m) x (-l,l).  The 4x spectrum (17 GB at 256^3, 137 GB at 512^3) is generated /
+// gathered in x-slot chunks, each chunk goes through the pruned inverse z and y passes at once (those lines are
+// complete inside a chunk), then x; the 2n x 2m x 2l kernel is transformed back with unpadded forward passes.
+// On return op->d_G holds G2 in the z-pass chunk layout of the nr = 2 kernels, scaled by 1/(8 n m l).
+int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_fy, const int* d_fz, GenParams p) {
+    const long n = op->n, m = op->m, l = op->l;
+    cudaStream_t s = op->stream;
+    cudaError_t e = cudaSuccess;
+    int rc;
+    int C = 1;
+    while ((double)(64.0 * n * m * l * 16.0) / C > 20e9 && (4 * n) / (2 * C) >= 8) C *= 2;
+    const long nelc = 4 * n / C;
+    cd *g4c = nullptr, *t1c = nullptr, *T2 = nullptr, *g2 = nullptr, *X = nullptr;
+    if ((rc = op->dmalloc((void**)&T2, (size_t)(4 * n) * (2 * m) * (2 * l) * sizeof(cd)))) return rc;
+    if ((rc = op->dmalloc((void**)&g4c, (size_t)nelc * (4 * m) * (4 * l) * sizeof(cd)))) return rc;
+    if ((rc = op->dmalloc((void**)&t1c, (size_t)nelc * (4 * m) * (2 * l) * sizeof(cd)))) return rc;
+    for (int c = 0; c < C; ++c) {
+        p.nel = nelc; p.sx0 = c * nelc;
+        k_fill_g3d<<<148 * 16, 256, 0, s>>>(d_gin, g4c, d_fx, d_fy, d_fz, p);
+        for (int cb = 0; cb <= 3; cb += 3) {     // (1) inverse z on the chunk: t1c[L + nelc*4m*jz2], L = sxl + nelc*sy4
+            LineAddr la{8, 1, 32 * l, 8, 1, 8, nelc * 4 * m};
+            la.nr = 4; la.cblock = cb;
+            cd* outp = t1c + (cb ? l * (nelc * 4 * m) : 0);
+#define Z1(N) launch_inv<N, true>(s, nelc * 4 * m, g4c, nullptr, outp, op->d_TABl, 1.0, la)
+            LS3_DISPATCH(l, Z1);
+            LS_CUDA_TRY(e);
+        }
+        for (int cb = 0; cb <= 3; cb += 3) {     // (2) inverse y: T2[sx4 + 4n*(jy2 + 2m*jz2)]
+            LineAddr la{nelc, 1, nelc * 4 * m, nelc, 1, 4 * n * 2 * m, 4 * n};
+            la.nr = 4; la.cblock = cb;
+            cd* outp = T2 + c * nelc + (cb ? m * 4 * n : 0);
+#define Y1(N) launch_inv<N, true>(s, nelc * 2 * l, t1c, nullptr, outp, op->d_TABm, 1.0, la)
+            LS3_DISPATCH(m, Y1);
+            LS_CUDA_TRY(e);
+        }
+    }
+    LS_CUDA_TRY(cudaStreamSynchronize(s));
+    op->dfree(g4c);
+    op->dfree(t1c);
+    if ((rc = op->dmalloc((void**)&g2, (size_t)(2 * n) * (2 * m) * (2 * l) * sizeof(cd)))) return rc;
+    for (int cb = 0; cb <= 3; cb += 3) {         // (3) inverse x: g2[jx2 + 2n*(jy2 + 2m*jz2)]
+        LineAddr la{1L << 40, 4 * n, 0, 1, 2 * n, 0, 1};
+        la.nr = 4; la.cblock = cb;
+        cd* outp = g2 + (cb ? n : 0);
+#define X1(N) launch_inv<N, false>(s, 2 * m * 2 * l, T2, nullptr, outp, op->d_TABn, 1.0, la)
+        LS3_DISPATCH(n, X1);
+        LS_CUDA_TRY(e);
+    }
+    LS_CUDA_TRY(cudaStreamSynchronize(s));
+    op->dfree(T2);
+    if ((rc = op->dmalloc((void**)&X, (size_t)(2 * n) * (2 * m) * (2 * l) * sizeof(cd)))) return rc;
+    {   // (4) forward x on the unpadded 2n-point lines: X[sx2 + 2n*line]
+        LineAddr la{1L << 40, 2 * n, 0, 1, 2 * n, 0, 1};
+        la.nr = 2; la.full2 = 1;
+#define X2(N) launch_fwd<N, false>(s, 2 * m * 2 * l, g2, nullptr, X, op->d_TABn, la)
+        LS3_DISPATCH(n, X2);
+        LS_CUDA_TRY(e);
+    }
+    {   // (5) forward y, lines (sx2, jz2): X -> g2 (as Y[sx2 + 2n*(sy2 + 2m*jz2)])
+        LineAddr la{2 * n, 1, 2 * n * 2 * m, 2 * n, 1, 2 * n * 2 * m, 2 * n};
+        la.nr = 2; la.full2 = 1;
+#define Y2(N) launch_fwd<N, true>(s, 2 * n * 2 * l, X, nullptr, g2, op->d_TABm, la)
+        LS3_DISPATCH(m, Y2);
+        LS_CUDA_TRY(e);
+    }
+    {   // (6) forward z, lines L = sx2 + 2n*sy2: Y -> G2[((L/8)*2 + rz)*8l + sz*8 + L%8]
+        LineAddr la{8, 1, 8, 2 * n * 2 * m, 1, 16 * l, 8};
+        la.nr = 2; la.full2 = 1;
+#define Z2(N) launch_fwd<N, true>(s, 2 * n * 2 * m, g2, nullptr, X, op->d_TABl, la)
+        LS3_DISPATCH(l, Z2);
+        LS_CUDA_TRY(e);
+    }
+    k_scale3<<<148 * 8, 256, 0, s>>>(X, (2 * n) * (2 * m) * (2 * l), 1.0 / (8.0 * (double)n * (double)m * (double)l));
+    LS_CUDA_TRY(cudaStreamSynchronize(s));
+    op->dfree(g2);
+    op->d_G = X;
+    op->nr = 2;
+    return LS_OK;
+}
+
 int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
              const double* nu, const ls_cdouble* gfft, double omega, double L, double Lp,
-             int rank, int nranks, const void* nccl_id) {
+             int rank, int nranks, const void* nccl_id, int flags) {
     LS_REQUIRE(out && nu, LS_ERR_INVALID, "ls_op3d_create: null pointer");
     LS_REQUIRE(n > 0 && m > 0 && l > 0, LS_ERR_INVALID, "ls_op3d_create: non-positive size");
     LS_REQUIRE(ne == 4 * n && me == 4 * m && le == 4 * l, LS_ERR_INVALID,
@@ -231,7 +325,9 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
             return LS_ERR_NCCL;
         }
     }
-    const long nel = op->nel, lloc = op->lloc;
+    const bool compact = (nranks == 1) && !(flags & LS_FLAG_PAD4);    // sharded operators keep the literal 4x padding for now
+    long nel = op->nel;
+    const long lloc = op->lloc;
     const size_t Nloc = (size_t)n * m * lloc, NEloc = (size_t)nel * me * le;
 #define TRY(x) do { rc = (x); if (rc) { delete op; return rc; } } while (0)
     TRY(op->dupload((void**)&op->d_nu, nu, Nloc * sizeof(double)));
@@ -249,7 +345,7 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
         TRY(op->dupload((void**)&d_fy, fy.data(), fy.size() * sizeof(int)));
         TRY(op->dupload((void**)&d_fz, fz.data(), fz.size() * sizeof(int)));
         if (gfft) TRY(op->dupload((void**)&d_gin, gfft, (size_t)ne * me * le * sizeof(cd)));
-        TRY(op->dmalloc((void**)&op->d_G, NEloc * sizeof(cd)));
+        if (!compact) TRY(op->dmalloc((void**)&op->d_G, NEloc * sizeof(cd)));
         GenParams p;
         p.n = n; p.m = m; p.l = l; p.ne = ne; p.me = me; p.le = le;
         p.nel = nel; p.sx0 = (long)rank * nel;
@@ -257,15 +353,18 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
         p.L = L; p.k = omega;
         p.eLk_re = cos(L * omega); p.eLk_im = sin(L * omega);
         p.scale = 1.0 / ((double)ne * (double)me * (double)le);
-        k_fill_g3d<<<148 * 16, 256, 0, op->stream>>>(d_gin, op->d_G, d_fx, d_fy, d_fz, p);
+        if (compact) TRY(compact_spectrum3d(op, d_gin, d_fx, d_fy, d_fz, p));
+        else k_fill_g3d<<<148 * 16, 256, 0, op->stream>>>(d_gin, op->d_G, d_fx, d_fy, d_fz, p);
         cudaError_t e = cudaStreamSynchronize(op->stream);
         if (e != cudaSuccess) { set_error("spectrum setup failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
         if (d_gin) op->dfree(d_gin);
         op->dfree(d_fx); op->dfree(d_fy); op->dfree(d_fz);
     }
-    TRY(op->dmalloc((void**)&op->d_A1, (size_t)ne * m * lloc * sizeof(cd)));
+    op->pn = op->nr * n; op->pm = op->nr * m; op->pl = op->nr * l;
+    op->nel = nel = op->pn / nranks;
+    TRY(op->dmalloc((void**)&op->d_A1, (size_t)op->pn * m * lloc * sizeof(cd)));
     if (nranks > 1) TRY(op->dmalloc((void**)&op->d_A1T, (size_t)nel * m * l * sizeof(cd)));
-    TRY(op->dmalloc((void**)&op->d_A2, (size_t)nel * me * l * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_A2, (size_t)nel * op->pm * l * sizeof(cd)));
 #undef TRY
     *out = reinterpret_cast<ls_handle>(op);
     return LS_OK;
@@ -279,13 +378,12 @@ extern "C" {
 
 int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_t me, int64_t le,
                    const double* nu, const ls_cdouble* gfft, double omega, double L, double Lp, int flags) {
-    (void)flags;
-    return create3d(out, n, m, l, ne, me, le, nu, gfft, omega, L, Lp, 0, 1, nullptr);
+    return create3d(out, n, m, l, ne, me, le, nu, gfft, omega, L, Lp, 0, 1, nullptr, flags);
 }
 
 int ls_op3d_create_dist(ls_handle* out, int64_t n, int64_t m, int64_t l, const double* nu_slab, double omega,
                         double L, double Lp, int rank, int nranks, const void* nccl_unique_id) {
-    return create3d(out, n, m, l, 4 * n, 4 * m, 4 * l, nu_slab, nullptr, omega, L, Lp, rank, nranks, nccl_unique_id);
+    return create3d(out, n, m, l, 4 * n, 4 * m, 4 * l, nu_slab, nullptr, omega, L, Lp, rank, nranks, nccl_unique_id, 0);
 }
 
 int ls_nccl_unique_id(void* out128) {

@@ -162,7 +162,7 @@ class FastM3D(_Handle):
     added so that gmres! (which needs them) takes the operator.
     """
 
-    def __init__(self, GFFT, nu, ne, me, le, n, m, l, k, quadRule="Greengard_Vico", L=None, Lp=None):
+    def __init__(self, GFFT, nu, ne, me, le, n, m, l, k, quadRule="Greengard_Vico", L=None, Lp=None, pad4=False):
         super().__init__()
         self.ne, self.me, self.le, self.n, self.m, self.l = (int(v) for v in (ne, me, le, n, m, l))
         self.omega = float(k)
@@ -184,7 +184,7 @@ class FastM3D(_Handle):
             g = np.asfortranarray(GFFT.astype(np.complex128, copy=False))
             gp = C.c_void_p(g.ctypes.data)
         check(lib().ls_op3d_create(C.byref(self._h), self.n, self.m, self.l, self.ne, self.me, self.le, ptr(nu), gp,
-                                   self.omega, float(L or 0.0), float(Lp or 0.0), 0))
+                                   self.omega, float(L or 0.0), float(Lp or 0.0), 2 if pad4 else 0))
 
     def size(self, dim=None):
         if dim is not None:

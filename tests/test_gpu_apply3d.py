@@ -137,3 +137,20 @@ def test_general_sizes_example3d_as_shipped(n, l):
         xg, hg = ls.gmres_(np.zeros(N, complex), Mg, rhs, maxiter=25, log=True)
         assert hg.iters == len(hist_o)
         assert np.max(np.abs(hg["resnorm"] - hist_o) / hist_o) < 1e-8
+
+
+@pytest.mark.parametrize("n,l", [(64, 64), (64, 128)])
+def test_compact_padding_equals_literal_4x_3d(n, l):
+    """Default 3-D handles run with 2x padding on the kernel restricted to the needed lags; pad4=True is the
+    reference's literal 4x evaluation."""
+    import fast_solver_lippmann_schwinger_b200 as ls
+    h, k, Mo = _problem(n, l)
+    A2 = ls.FastM3D(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.le, n, n, l, k)
+    A4 = ls.FastM3D(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.le, n, n, l, k, pad4=True)
+    N = n * n * l
+    rng = np.random.default_rng(n + l)
+    b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    y2, y4, ref = A2 * b, A4 * b, Mo * b
+    assert _rel(y2, ref) <= TOL and _rel(y4, ref) <= TOL
+    assert _rel(y2 - b, y4 - b) <= 1e-12
+    assert A2.launch_count() == 5 and A4.launch_count() == 5
