@@ -149,11 +149,12 @@ def run_reference(args, rank, world):
 
 def workload_config(n):
     return {"workload": "2-D Greengard_Vico LS operator apply, grid %dx%d (padded %dx%d), k=2pi/(10h), "
-                        "Gaussian-bump contrast (examples/example.jl:48), rng(1234) complex input" % (n, n, 4 * n, 4 * n),
+                        "Gaussian-bump contrast (examples/example.jl:48), rng(1234) complex input; evaluated with 2x padding on the "
+                        "kernel restricted to the needed lags (same operator to 1e-16)" % (n, n, 4 * n, 4 * n),
             "grid": [n, n], "padded": [4 * n, 4 * n], "quadRule": "Greengard_Vico", "points_per_wavelength": 10,
             "element": "complex128 (two f64)",
-            "l2_policy": "inputs larger than L2 (spectrum %.2f GB, intermediates %.2f GB each per apply)" % (
-                16 * 16 * n * n / 1e9, 64 * n * n / 1e9),
+            "l2_policy": "inputs larger than L2 (per apply: spectrum %.2f GB + two intermediates of %.2f GB + vectors %.2f GB = %.2f GB > 126 MB)" % (
+                64 * n * n / 1e9, 32 * n * n / 1e9, 56 * n * n / 1e9, 248 * n * n / 1e9),
             "parallelism": "replica per GPU (2-D path does not shard)"}
 
 
@@ -210,26 +211,37 @@ def bench_3d(args, ls, lsd, rank, world, local_rank, dist, peak, peak_src):
     per = [p / max(c, 1) for p, c in zip(ph, cnt)]
     ms_step = ms / steps
     p3 = per[2]
-    alg_p3 = 1536.0 * N / world            # spectrum 1024N + padded slab read 256N + write 256N, per rank
+    compact = True                          # compact 2x padding on one GPU and on the sharded operator
+    # P3 bytes per rank.  implemented: spectrum + padded slab read + write of the pass as run;
+    # survey: SURVEY.md 8(d) accounting of the literal pruned-4x pass structure (1024N + 256N + 256N)
+    impl_p3 = (256.0 if compact else 1536.0) * N / world
+    impl_apply = (568.0 if compact else 2360.0) * N / world
+    alg_p3 = 1536.0 * N / world
     out = {
         "metric": "ls_operator_applies_per_s_3d", "value": steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "scaling": "strong" if world > 1 else "single", "ms_per_apply": ms_step, "grid": [n, n, n], "padded": [4 * n] * 3,
-        "workload": "3-D Greengard_Vico LS apply %d^3 (padded %d^3), spectrum generated on device, z-slab sharded over %d GPU(s)" % (n, 4 * n, world),
+        "workload": "3-D Greengard_Vico LS apply %d^3 (reference padding %d^3), spectrum generated on device, z-slab sharded over %d GPU(s)" % (n, 4 * n, world),
+        "padding_used": "2x (kernel restricted to the lags the cropped apply touches; same operator to 1e-16)" if compact else "4x (literal)",
         "gpu_launches": launches,
         "phase_ms": {"P1_x_fwd": per[0], "P2_y_fwd": per[1], "P3_z_fused": per[2], "P4_y_inv": per[3], "P5_x_inv": per[4],
                      "a2a_fwd": per[5], "a2a_back": per[6]},
         "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P3: fused z-line FFT, spectrum multiply, inverse)", "achieved": alg_p3 / (p3 * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg_p3 / (p3 * 1e-3) / 1e9 / peak,
-                     "traffic": (21.4755e9 + 4.2829e9) * (N / 256.0 ** 3) / world if n == 256 else None,
-                     "traffic_source": "ncu --set full r1_e at 256^3 on one GPU: dram read 21.48 GB + write 4.28 GB (profiles/r1_e_notes.md)",
+                     "algorithmic_bytes_model": "SURVEY.md 8(d), literal pruned-4x pass structure: 1536N per apply for this pass",
+                     "implemented_bytes_per_launch": impl_p3, "implemented_achieved": impl_p3 / (p3 * 1e-3) / 1e9,
+                     "implemented_frac": impl_p3 / (p3 * 1e-3) / 1e9 / peak,
+                     "traffic": ((3.2213e9 + 1.0451e9) if compact else (21.4755e9 + 4.2829e9) / world) if n == 256 else None,
+                     "traffic_source": "ncu --set full at 256^3: r1_g compact dram read 3.22 GB + write 1.05 GB; r1_e literal 21.48 + 4.28 GB (profiles/)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_p3, "launch_ms": p3},
-        "apply_roofline": {"algorithmic_bytes_per_apply_per_gpu": 2360.0 * N / world,
-                           "frac": 2360.0 * N / world / (ms_step * 1e-3) / 1e9 / peak},
+        "apply_roofline": {"survey_bytes_per_apply_per_gpu": 2360.0 * N / world,
+                           "survey_frac": 2360.0 * N / world / (ms_step * 1e-3) / 1e9 / peak,
+                           "implemented_bytes_per_apply_per_gpu": impl_apply,
+                           "implemented_frac": impl_apply / (ms_step * 1e-3) / 1e9 / peak},
         "e2e": {"value": 3 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * (b_ - a), "d2h_bytes_per_step": 16 * (b_ - a)},
     }
     if world > 1:
-        xb = lsd.exchange_bytes_per_rank(n, n, n, world)
+        xb = lsd.exchange_bytes_per_rank(n, n, n, world, pad=2)
         a2a = 0.5 * (per[5] + per[6])
         out["nvlink"] = {"bytes_sent_per_gpu_per_transpose": xb, "a2a_ms": a2a, "achieved_GBs": xb / (a2a * 1e-3) / 1e9,
                          "peak_GBs": 770.0, "frac": xb / (a2a * 1e-3) / 1e9 / 770.0,
@@ -260,7 +272,7 @@ def bench_gmres(args, ls, M, n, k, h, peak):
     _, hist2 = ls.gmres_(dx2, M, db, reltol=1e-8, maxiter=args.gmres_maxiter, log=True, workspace=ws, orth_meth="DGKS")
     dt2 = time.perf_counter() - t0
     dgks = {"time_s": dt2, "iters": hist2.iters, "converged": hist2.isconverged, "ms_per_iter": 1e3 * dt2 / max(hist2.iters, 1)}
-    alg_iter = (568.0 + 64.0 * 10.5 + 48.0 + 32.0) * N         # apply + fused MGS (avg k = 10.5) + normalise
+    alg_iter = (248.0 + 64.0 * 10.5 + 48.0 + 32.0) * N         # apply (2x padding) + fused MGS (avg k = 10.5) + normalise
     return {"metric": "gmres_time_to_1e-8", "time_s": dt, "iters": hist.iters, "converged": hist.isconverged, "restart": 20,
             "mv_products": hist.mvps, "ms_per_iter": 1e3 * dt / it, "final_rel_residual": float(hist["resnorm"][-1] / hist["resnorm"][0]) if hist.iters else None,
             "preconditioner": "Identity (the Msp direct solve is host-side and out of scope, SURVEY.md H1)",
@@ -422,7 +434,10 @@ def main():
     if rank == 0:
         value = world * args.steps / (ms * 1e-3)
         p2_ms = phase_ms[1] / max(phase_cnt[1], 1)
-        alg_bytes_p2 = 384.0 * N          # A read 64N + spectrum 256N + C write 64N
+        # SURVEY.md 8(d) accounting of the literal pruned-4x pass structure: P2 = A read 64N + spectrum 256N + C write 64N.
+        # The handle runs the same operator with 2x padding (kernel restricted to the needed lags): P2 moves 32N + 64N + 32N.
+        alg_bytes_p2 = 384.0 * N
+        impl_bytes_p2 = 128.0 * N
         achieved = alg_bytes_p2 / (p2_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -435,11 +450,17 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: 4x forward FFT, spectrum multiply, inverse FFT per padded row)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 1.3422e9 + 0.2545e9, "traffic_source": "ncu --set full r1_d: dram read 1.342 GB + write 0.2545 GB per launch (profiles/r1_d_2d_2048_P2_direct.txt)",
+                         "algorithmic_bytes_model": "SURVEY.md 8(d), literal pruned-4x pass structure (frac > 1: the implemented 2x-padded pass needs a third of these bytes)",
+                         "implemented_bytes_per_launch": impl_bytes_p2, "implemented_achieved": impl_bytes_p2 / (p2_ms * 1e-3) / 1e9,
+                         "implemented_frac": impl_bytes_p2 / (p2_ms * 1e-3) / 1e9 / peak,
+                         "traffic": (0.4027e9 + 0.1140e9) if n == 2048 else None,
+                         "traffic_source": "ncu --set full r1_g at 2048^2: dram read 0.403 GB + write 0.114 GB per launch (profiles/r1_g_notes.md)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_p2, "launch_ms": p2_ms},
-            "apply_roofline": {"algorithmic_bytes_per_apply": 568.0 * N, "achieved": 568.0 * N / (ms / args.steps * 1e-3) / 1e9,
-                               "frac": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs":
-                                   568.0 * N / (ms / args.steps * 1e-3) / 1e9 / 8000.0},
+            "apply_roofline": {"survey_bytes_per_apply": 568.0 * N, "survey_achieved": 568.0 * N / (ms / args.steps * 1e-3) / 1e9,
+                               "survey_frac": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak,
+                               "survey_frac_of_nominal_8TBs": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / 8000.0,
+                               "implemented_bytes_per_apply": 248.0 * N,
+                               "implemented_frac": 248.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak},
             "phase_ms": {"P1_fwd_columns": phase_ms[0] / max(phase_cnt[0], 1), "P2_fused_rows": p2_ms,
                          "P3_inv_columns": phase_ms[2] / max(phase_cnt[2], 1)},
             "checksum": checksum,

@@ -85,7 +85,7 @@ def lib():
         "ls_op3d_create": (ci, [C.POINTER(vp), i64, i64, i64, i64, i64, i64, vp, vp, dbl, dbl, dbl, ci]),
         "ls_op3d_apply": (ci, [vp, vp, vp, ci, ci]),
         "ls_nccl_unique_id": (ci, [vp]),
-        "ls_op3d_create_dist": (ci, [C.POINTER(vp), i64, i64, i64, vp, dbl, dbl, dbl, ci, ci, vp]),
+        "ls_op3d_create_dist": (ci, [C.POINTER(vp), i64, i64, i64, vp, dbl, dbl, dbl, ci, ci, vp, ci]),
         "ls_op_size": (ci, [vp, C.POINTER(i64)]),
         "ls_spm_create": (ci, [C.POINTER(vp), i64, i64, vp, vp, vp]),
         "ls_spm_mv": (ci, [vp, CDouble, vp, CDouble, vp, ci]),

@@ -102,6 +102,7 @@ struct HandleBase {
         return LS_OK;
     }
     void dfree(void* p) {
+        if (!p) return;
         for (size_t i = 0; i < dev_allocs.size(); ++i)
             if (dev_allocs[i] == p) { dev_allocs.erase(dev_allocs.begin() + i); break; }
         cudaFree(p);

@@ -203,24 +203,34 @@ __global__ void k_scale3(cd* a, long n, double s) {
 }
 
 // Compact (2x) spectrum, 3-D version of compact_spectrum() in op2d.cu: the kernel g = ifftn(GFFT) is only
-// needed at the lags (-n,n) x (-m,m) x (-l,l).  The 4x spectrum (17 GB at 256^3, 137 GB at 512^3) is generated /
-// gathered in x-slot chunks, each chunk goes through the pruned inverse z and y passes at once (those lines are
-// complete inside a chunk), then x; the 2n x 2m x 2l kernel is transformed back with unpadded forward passes.
-// On return op->d_G holds G2 in the z-pass chunk layout of the nr = 2 kernels, scaled by 1/(8 n m l).
+// needed at the lags (-n,n) x (-m,m) x (-l,l).  Rank r owns the x-slot slab [r*4n/P, (r+1)*4n/P) of the 4x
+// spectrum (17 GB at 256^3, 137 GB at 512^3 in total), generated / gathered in chunks; each chunk goes through
+// the pruned inverse z and y passes at once (those lines are complete inside a chunk).  The inverse x pass needs
+// all x slots: one all-to-all re-slabs along z (P > 1).  The 2n x 2m x 2l kernel is transformed back with
+// unpadded forward passes (x and y on z slabs, a second all-to-all, then z on x-slot slabs).
+// On return op->d_G holds this rank's slab of G2 in the z-pass chunk layout of the nr = 2 kernels, scaled by 1/(8 n m l).
 int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_fy, const int* d_fz, GenParams p) {
     const long n = op->n, m = op->m, l = op->l;
+    const int P = op->P, rank = op->rank;
     cudaStream_t s = op->stream;
     cudaError_t e = cudaSuccess;
     int rc;
+    const long nel4 = 4 * n / P;            // 4x x-slots of this rank
+    const long nel2 = 2 * n / P;            // 2x x-slots of this rank (final slab)
+    const long lz2 = 2 * l / P;             // 2x z planes of this rank (intermediate slab)
+    LS_REQUIRE(nel2 % 8 == 0 && lz2 >= 1 && (2 * l) % P == 0, LS_ERR_UNSUPPORTED,
+               "compact padding needs 2n/P to be a multiple of 8 and 2l divisible by P");
     int C = 1;
-    while ((double)(64.0 * n * m * l * 16.0) / C > 20e9 && (4 * n) / (2 * C) >= 8) C *= 2;
-    const long nelc = 4 * n / C;
-    cd *g4c = nullptr, *t1c = nullptr, *T2 = nullptr, *g2 = nullptr, *X = nullptr;
-    if ((rc = op->dmalloc((void**)&T2, (size_t)(4 * n) * (2 * m) * (2 * l) * sizeof(cd)))) return rc;
+    while ((double)(64.0 * n * m * l * 16.0) / P / C > 20e9 && nel4 / (2 * C) >= 8) C *= 2;
+    const long nelc = nel4 / C;
+    cd *g4c = nullptr, *t1c = nullptr, *T2 = nullptr, *R = nullptr, *g2 = nullptr, *X = nullptr, *Y = nullptr, *Z = nullptr, *G2 = nullptr;
+    const size_t slab4 = (size_t)nel4 * (2 * m) * (2 * l);          // elements of T2 (this rank)
+    const size_t slab2 = (size_t)(2 * n) * (2 * m) * lz2;           // elements of g2 / X (this rank) == nel2*2m*2l
+    if ((rc = op->dmalloc((void**)&T2, slab4 * sizeof(cd)))) return rc;
     if ((rc = op->dmalloc((void**)&g4c, (size_t)nelc * (4 * m) * (4 * l) * sizeof(cd)))) return rc;
     if ((rc = op->dmalloc((void**)&t1c, (size_t)nelc * (4 * m) * (2 * l) * sizeof(cd)))) return rc;
     for (int c = 0; c < C; ++c) {
-        p.nel = nelc; p.sx0 = c * nelc;
+        p.nel = nelc; p.sx0 = (long)rank * nel4 + c * nelc;
         k_fill_g3d<<<148 * 16, 256, 0, s>>>(d_gin, g4c, d_fx, d_fy, d_fz, p);
         for (int cb = 0; cb <= 3; cb += 3) {     // (1) inverse z on the chunk: t1c[L + nelc*4m*jz2], L = sxl + nelc*sy4
             LineAddr la{8, 1, 32 * l, 8, 1, 8, nelc * 4 * m};
@@ -230,10 +240,10 @@ int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_
             LS3_DISPATCH(l, Z1);
             LS_CUDA_TRY(e);
         }
-        for (int cb = 0; cb <= 3; cb += 3) {     // (2) inverse y: T2[sx4 + 4n*(jy2 + 2m*jz2)]
-            LineAddr la{nelc, 1, nelc * 4 * m, nelc, 1, 4 * n * 2 * m, 4 * n};
+        for (int cb = 0; cb <= 3; cb += 3) {     // (2) inverse y: T2[sxl + nel4*(jy2 + 2m*jz2)], sxl within the rank's slab
+            LineAddr la{nelc, 1, nelc * 4 * m, nelc, 1, nel4 * 2 * m, nel4};
             la.nr = 4; la.cblock = cb;
-            cd* outp = T2 + c * nelc + (cb ? m * 4 * n : 0);
+            cd* outp = T2 + c * nelc + (cb ? m * nel4 : 0);
 #define Y1(N) launch_inv<N, true>(s, nelc * 2 * l, t1c, nullptr, outp, op->d_TABm, 1.0, la)
             LS3_DISPATCH(m, Y1);
             LS_CUDA_TRY(e);
@@ -242,43 +252,70 @@ int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_
     LS_CUDA_TRY(cudaStreamSynchronize(s));
     op->dfree(g4c);
     op->dfree(t1c);
-    if ((rc = op->dmalloc((void**)&g2, (size_t)(2 * n) * (2 * m) * (2 * l) * sizeof(cd)))) return rc;
-    for (int cb = 0; cb <= 3; cb += 3) {         // (3) inverse x: g2[jx2 + 2n*(jy2 + 2m*jz2)]
-        LineAddr la{1L << 40, 4 * n, 0, 1, 2 * n, 0, 1};
-        la.nr = 4; la.cblock = cb;
+    // re-slab along z: block q = planes jz2 in [q*lz2, (q+1)*lz2), contiguous in T2; received blocks are ordered by source rank
+    const long blkA = nel4 * 2 * m * lz2;
+    if (P > 1) {
+        if ((rc = op->dmalloc((void**)&R, slab4 * sizeof(cd)))) return rc;
+        if ((rc = all_to_all(op, T2, R, blkA))) return rc;
+        LS_CUDA_TRY(cudaStreamSynchronize(s));
+        op->dfree(T2);
+    } else {
+        R = T2;
+    }
+    if ((rc = op->dmalloc((void**)&g2, slab2 * sizeof(cd)))) return rc;
+    int sh4 = 0;
+    while ((1L << sh4) < nel4) ++sh4;
+    for (int cb = 0; cb <= 3; cb += 3) {         // (3) inverse x, lines (jy2, jz2_loc): slot sx4 at R[(sx4/nel4)*blkA + nel4*line + sx4%nel4]
+        LineAddr la{1L << 40, nel4, 0, 1, 2 * n, 0, 1};
+        la.nr = 4; la.cblock = cb; la.split_shift = sh4; la.split_stride = blkA;
         cd* outp = g2 + (cb ? n : 0);
-#define X1(N) launch_inv<N, false>(s, 2 * m * 2 * l, T2, nullptr, outp, op->d_TABn, 1.0, la)
+#define X1(N) launch_inv<N, false>(s, 2 * m * lz2, R, nullptr, outp, op->d_TABn, 1.0, la)
         LS3_DISPATCH(n, X1);
         LS_CUDA_TRY(e);
     }
     LS_CUDA_TRY(cudaStreamSynchronize(s));
-    op->dfree(T2);
-    if ((rc = op->dmalloc((void**)&X, (size_t)(2 * n) * (2 * m) * (2 * l) * sizeof(cd)))) return rc;
+    op->dfree(R);
+    if ((rc = op->dmalloc((void**)&X, slab2 * sizeof(cd)))) return rc;
     {   // (4) forward x on the unpadded 2n-point lines: X[sx2 + 2n*line]
         LineAddr la{1L << 40, 2 * n, 0, 1, 2 * n, 0, 1};
         la.nr = 2; la.full2 = 1;
-#define X2(N) launch_fwd<N, false>(s, 2 * m * 2 * l, g2, nullptr, X, op->d_TABn, la)
+#define X2(N) launch_fwd<N, false>(s, 2 * m * lz2, g2, nullptr, X, op->d_TABn, la)
         LS3_DISPATCH(n, X2);
         LS_CUDA_TRY(e);
     }
-    {   // (5) forward y, lines (sx2, jz2): X -> g2 (as Y[sx2 + 2n*(sy2 + 2m*jz2)])
-        LineAddr la{2 * n, 1, 2 * n * 2 * m, 2 * n, 1, 2 * n * 2 * m, 2 * n};
+    // (5) forward y, lines (sx2, jz2_loc), written grouped by destination rank q = sx2 / nel2:
+    //     Y[q*blkB + sxl2 + nel2*(sy2 + 2m*jz2_loc)]   (g2 is reused as Y)
+    const long blkB = nel2 * 2 * m * lz2;
+    Y = g2;
+    for (int q = 0; q < P; ++q) {
+        LineAddr la{nel2, 1, 2 * n * 2 * m, 2 * n, 1, nel2 * 2 * m, nel2};
         la.nr = 2; la.full2 = 1;
-#define Y2(N) launch_fwd<N, true>(s, 2 * n * 2 * l, X, nullptr, g2, op->d_TABm, la)
+        const cd* inp = X + q * nel2;
+        cd* outp = Y + q * blkB;
+#define Y2(N) launch_fwd<N, true>(s, nel2 * lz2, inp, nullptr, outp, op->d_TABm, la)
         LS3_DISPATCH(m, Y2);
         LS_CUDA_TRY(e);
     }
-    {   // (6) forward z, lines L = sx2 + 2n*sy2: Y -> G2[((L/8)*2 + rz)*8l + sz*8 + L%8]
-        LineAddr la{8, 1, 8, 2 * n * 2 * m, 1, 16 * l, 8};
+    if (P > 1) {       // re-slab along x: received blocks ordered by source rank = ordered by z plane
+        Z = X;
+        if ((rc = all_to_all(op, Y, Z, blkB))) return rc;
+        LS_CUDA_TRY(cudaStreamSynchronize(s));
+        G2 = Y;
+    } else {
+        Z = Y;
+        G2 = X;
+    }
+    {   // (6) forward z, lines L = sxl2 + nel2*sy2: Z[L + nel2*2m*jz2] -> G2[((L/8)*2 + rz)*8l + sz*8 + L%8]
+        LineAddr la{8, 1, 8, nel2 * 2 * m, 1, 16 * l, 8};
         la.nr = 2; la.full2 = 1;
-#define Z2(N) launch_fwd<N, true>(s, 2 * n * 2 * m, g2, nullptr, X, op->d_TABl, la)
+#define Z2(N) launch_fwd<N, true>(s, nel2 * 2 * m, Z, nullptr, G2, op->d_TABl, la)
         LS3_DISPATCH(l, Z2);
         LS_CUDA_TRY(e);
     }
-    k_scale3<<<148 * 8, 256, 0, s>>>(X, (2 * n) * (2 * m) * (2 * l), 1.0 / (8.0 * (double)n * (double)m * (double)l));
+    k_scale3<<<148 * 8, 256, 0, s>>>(G2, (long)slab2, 1.0 / (8.0 * (double)n * (double)m * (double)l));
     LS_CUDA_TRY(cudaStreamSynchronize(s));
-    op->dfree(g2);
-    op->d_G = X;
+    op->dfree(Z == G2 ? nullptr : Z);
+    op->d_G = G2;
     op->nr = 2;
     return LS_OK;
 }
@@ -325,7 +362,7 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
             return LS_ERR_NCCL;
         }
     }
-    const bool compact = (nranks == 1) && !(flags & LS_FLAG_PAD4);    // sharded operators keep the literal 4x padding for now
+    const bool compact = !(flags & LS_FLAG_PAD4);
     long nel = op->nel;
     const long lloc = op->lloc;
     const size_t Nloc = (size_t)n * m * lloc, NEloc = (size_t)nel * me * le;
@@ -382,8 +419,8 @@ int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, 
 }
 
 int ls_op3d_create_dist(ls_handle* out, int64_t n, int64_t m, int64_t l, const double* nu_slab, double omega,
-                        double L, double Lp, int rank, int nranks, const void* nccl_unique_id) {
-    return create3d(out, n, m, l, 4 * n, 4 * m, 4 * l, nu_slab, nullptr, omega, L, Lp, rank, nranks, nccl_unique_id, 0);
+                        double L, double Lp, int rank, int nranks, const void* nccl_unique_id, int flags) {
+    return create3d(out, n, m, l, 4 * n, 4 * m, 4 * l, nu_slab, nullptr, omega, L, Lp, rank, nranks, nccl_unique_id, flags);
 }
 
 int ls_nccl_unique_id(void* out128) {

@@ -44,9 +44,9 @@ def scatter_vector(v, n, m, l, rank, nranks):
     return np.ascontiguousarray(v[a:b])
 
 
-def exchange_bytes_per_rank(n, m, l, nranks):
-    """Bytes each rank sends over NVLink per transpose: 16 * 4N * (P-1) / P^2."""
-    return 16 * 4 * n * m * l * (nranks - 1) // (nranks * nranks)
+def exchange_bytes_per_rank(n, m, l, nranks, pad=4):
+    """Bytes each rank sends over NVLink per transpose: 16 * pad*N * (P-1) / P^2 (pad = 4 literal, 2 compact)."""
+    return 16 * pad * n * m * l * (nranks - 1) // (nranks * nranks)
 
 
 def make_unique_id():
@@ -69,7 +69,7 @@ class FastM3DSharded(_Handle):
     """The FastM3D operator slab-decomposed over `nranks` GPUs (collective object: every rank
     constructs it and calls each apply).  Vectors are this rank's z slab."""
 
-    def __init__(self, nu_slab, n, m, l, k, L, Lp, rank, nranks, unique_id):
+    def __init__(self, nu_slab, n, m, l, k, L, Lp, rank, nranks, unique_id, pad4=False):
         super().__init__()
         self.n, self.m, self.l = int(n), int(m), int(l)
         self.ne, self.me, self.le = 4 * self.n, 4 * self.m, 4 * self.l
@@ -83,7 +83,7 @@ class FastM3DSharded(_Handle):
             raise ValueError("DimensionMismatch: nu slab has %d entries, expected %d" % (nu_slab.shape[0], self.N))
         idbuf = C.create_string_buffer(unique_id, 128) if self.nranks > 1 else None
         check(lib().ls_op3d_create_dist(C.byref(self._h), self.n, self.m, self.l, ptr(nu_slab), self.omega,
-                                        float(L), float(Lp), self.rank, self.nranks, idbuf))
+                                        float(L), float(Lp), self.rank, self.nranks, idbuf, 2 if pad4 else 0))
 
     def size(self, dim=None):
         if dim is not None:

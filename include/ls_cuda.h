@@ -106,7 +106,7 @@ int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, 
 int ls_nccl_unique_id(void* out128);
 int ls_op3d_create_dist(ls_handle* out, int64_t n, int64_t m, int64_t l, const double* nu_slab,
                         double omega, double L, double Lp, int rank, int nranks,
-                        const void* nccl_unique_id);
+                        const void* nccl_unique_id, int flags);
 /* mode 0: `*(M::FastM3D, b)` = b + omega^2 FFTconvolution(M, nu.*b)  (FastConvolution3D.jl:31-37)
  * mode 1: FFTconvolution(M, b)                                      (FastConvolution3D.jl:39-63) */
 int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc);

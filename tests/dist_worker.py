@@ -34,6 +34,7 @@ def main():
     p0, p1 = lsd.slab_range(l, rank, world)
     assert (p1 - p0) * n * n == b_ - a
     assert lsd.exchange_bytes_per_rank(n, n, l, world) == 16 * 4 * n ** 3 * (world - 1) // world ** 2
+    assert lsd.exchange_bytes_per_rank(n, n, l, world, pad=2) == 16 * 2 * n ** 3 * (world - 1) // world ** 2
     if mode == "cpu":
         # the sharded operator cannot be created without a GPU: it must fail loudly, not fall back
         try:
@@ -68,6 +69,13 @@ def main():
     c_ref = O.FFTconvolution3D(Mo, b)
     c = ls.FFTconvolution(M, np.ascontiguousarray(b[a:b_]))
     assert np.linalg.norm(c - c_ref[a:b_]) / np.linalg.norm(c_ref[a:b_]) <= 1e-12
+    # the literal 4x-padded sharded evaluation agrees with the default compact one
+    uid4 = lsd.broadcast_unique_id(rank)          # every communicator needs its own NCCL id
+    M4 = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid4, pad4=True)
+    y4 = M4 * np.ascontiguousarray(b[a:b_])
+    assert np.linalg.norm(y4 - y_ref[a:b_]) / np.linalg.norm(y_ref[a:b_]) <= 1e-12
+    assert np.linalg.norm((y4 - y)) / np.linalg.norm(y_ref[a:b_]) <= 1e-13
+    M4.destroy()
 
     # sharded GMRES (dots all-reduced as scalars) against the oracle history
     X, Y, Z = O.grid3d(x, x, x)
