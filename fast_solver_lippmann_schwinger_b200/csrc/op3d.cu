@@ -1,20 +1,22 @@
 // 3-D Lippmann-Schwinger operator  y = b + omega^2 * G (nu .* b)  on one B200 (slab-ready layout).
 // Stands behind struct FastM3D, its `*` and FFTconvolution (reference FastConvolution3D.jl:7-63).
-// Five launches per apply (pruned 4x zero padding in every dimension, see line_kernels.cuh):
-//   P1 k_fwd_pruned<n,A>  x lines (contiguous)   b,nu [n m l]      -> A1 [ne m l]
-//   P2 k_fwd_pruned<m,B>  y lines (8 x-slots/warp quarter)  A1     -> A2 [ne me l]
-//   P3 k_mid_fused <l,B>  z lines, fused spectrum multiply, in place on A2 (reads G [ne me le])
-//   P4 k_inv_pruned<m,B>  y lines                 A2               -> C1 [ne m l]   (reuses A1)
+// Five launches per apply (pruned zero padding in every dimension, see line_kernels.cuh; padding
+// factor nr = 2 by default - the compact spectrum built at create time - or 4 with LS_FLAG_PAD4;
+// pn = nr*n etc.):
+//   P1 k_fwd_pruned<n,A>  x lines (contiguous)   b,nu [n m l]      -> A1 [pn m l]
+//   P2 k_fwd_pruned<m,B>  y lines (8 x-slots/warp quarter)  A1     -> A2 [pn pm l]
+//   P3 k_mid_fused <l,B>  z lines, fused spectrum multiply, in place on A2 (reads G [pn pm pl])
+//   P4 k_inv_pruned<m,B>  y lines                 A2               -> C1 [pn m l]   (reuses A1)
 //   P5 k_inv_pruned<n,A>  x lines + combine       C1, b            -> y
-// Algorithmic HBM bytes per apply: 2360*N; the spectrum read is 1024*N of it.
+// HBM bytes per apply: 568*N with nr = 2 (spectrum 128*N), 2360*N with nr = 4.
 //
 // Multi-GPU (one process per GPU, P = 2/4/8 ranks): the grid is split into z slabs (l/P planes per
 // rank, a contiguous range of the vector).  P1 runs on the local planes and writes its output
-// already grouped by destination rank; one NCCL all-to-all re-slabs the (most pruned) ne x m x l
-// array along the x-slot axis; P2-P4 run on the rank's ne/P x-slots against its slab of the
+// already grouped by destination rank; one NCCL all-to-all re-slabs the (most pruned) pn x m x l
+// array along the x-slot axis; P2-P4 run on the rank's pn/P x-slots against its slab of the
 // spectrum; a second all-to-all brings the result back to z slabs for P5.  Neither exchange needs
 // a pack or unpack pass: both sides read/write the exchange buffers in place (slot_off()).
-// All-to-all volume per rank and direction: 16*4N*(P-1)/P^2 bytes.
+// All-to-all volume per rank and direction: 16*nr*N*(P-1)/P^2 bytes.
 #include "ls_common.cuh"
 #include "line_kernels.cuh"
 #include "dist.cuh"
