@@ -76,6 +76,11 @@ struct LineAddr {
     // (s & (2^shift - 1))*es + (s >> shift)*split_stride.  shift = 62 disables it.
     int split_shift = 62;
     long split_stride = 0;
+    // optional second level (x-slot chunks inside a rank's slab, pipelined transposes): bits
+    // [split_shift, split2_shift) select the chunk (stride split_stride), bits >= split2_shift the
+    // rank (stride split2_stride).  split2_shift = 62 leaves the one-level rule above.
+    int split2_shift = 62;
+    long split2_stride = 0;
     // padding factor of the line: nr = 4 sub-transforms r = 0..3 (the reference's 4N zero padding) or
     // nr = 2 (r = 0, 2 in units of w_4N: a 2N padding, enough once the kernel is restricted to lags (-N, N))
     int nr = 4;
@@ -83,7 +88,9 @@ struct LineAddr {
     int full2 = 0;      // forward: the input line has 2N points (no zero padding), nr must be 2
 };
 __device__ __forceinline__ long slot_off(const LineAddr& a, long s, long es) {
-    return (s & ((1L << a.split_shift) - 1)) * es + (s >> a.split_shift) * a.split_stride;
+    return (s & ((1L << a.split_shift) - 1)) * es
+         + ((s & ((1L << a.split2_shift) - 1)) >> a.split_shift) * a.split_stride
+         + (s >> a.split2_shift) * a.split2_stride;
 }
 __device__ __forceinline__ long line_in(const LineAddr& a, long L) { return (L % a.ldim0) * a.in_ls0 + (L / a.ldim0) * a.in_ls1; }
 __device__ __forceinline__ long line_out(const LineAddr& a, long L) { return (L % a.ldim0) * a.out_ls0 + (L / a.ldim0) * a.out_ls1; }

@@ -63,16 +63,16 @@ struct HandleBase {
     bool profiling = false;
     struct PhaseEv { int phase; cudaEvent_t a, b; };
     std::vector<PhaseEv> phase_events;
-    void phase_begin(int phase) {
+    void phase_begin(int phase, cudaStream_t on = nullptr) {
         if (!profiling) return;
         PhaseEv pe; pe.phase = phase;
         cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
-        cudaEventRecord(pe.a, stream);
+        cudaEventRecord(pe.a, on ? on : stream);
         phase_events.push_back(pe);
     }
-    void phase_end() {
+    void phase_end(cudaStream_t on = nullptr) {
         if (!profiling) return;
-        cudaEventRecord(phase_events.back().b, stream);
+        cudaEventRecord(phase_events.back().b, on ? on : stream);
     }
 
     int init_base(uint32_t k) {

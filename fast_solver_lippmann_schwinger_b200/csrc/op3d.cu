@@ -38,14 +38,28 @@ struct Op3D : HandleBase {
     double* d_nu = nullptr;            // local z slab
     cd* d_G = nullptr;                 // [unit = (sxl + nel*sy)/8][rz][slot_z][8]  scaled by 1/(ne me le)
     cd *d_TABn = nullptr, *d_TABm = nullptr, *d_TABl = nullptr;
-    cd* d_A1 = nullptr;                // P1 output / P5 input: [dest rank][nel][m][lloc]   (= ne x m x l when P == 1)
-    cd* d_A1T = nullptr;               // re-slabbed: nel x m x l  (P > 1 only)
-    cd* d_A2 = nullptr;                // nel x me x l
+    // x-slot chunks: the rank's nel x-slots are handled as Cx chunks of nelc; the exchange buffers and the
+    // spectrum are chunk-major, so that chunk c's transposes (on cstream) overlap chunk c+-1's P2-P4.
+    int Cx = 1;
+    long nelc = 0;
+    cd* d_A1 = nullptr;                // P1 output / P5 input: [chunk][dest rank][nelc][m][lloc]
+    cd* d_A1T = nullptr;               // re-slabbed: [chunk][nelc x m x l]  (P > 1 only)
+    cd* d_A2 = nullptr;                // nelc x pm x l (one chunk, reused)
     cd* d_b = nullptr; cd* d_y = nullptr;
+    cudaStream_t cstream = nullptr;    // high-priority stream of the NCCL exchanges (P > 1)
+    cudaEvent_t evP1 = nullptr, evDone = nullptr;
+    std::vector<cudaEvent_t> evIn, evOut;
     int64_t op_size() const override { return n * m * lloc; }
     int apply_dev(const cd* b, cd* y, int mode) override;
     ncclComm_t nccl_comm() const override { return comm; }
-    ~Op3D() override { if (comm) ncclCommDestroy(comm); }
+    ~Op3D() override {
+        if (comm) ncclCommDestroy(comm);
+        for (auto ev : evIn) cudaEventDestroy(ev);
+        for (auto ev : evOut) cudaEventDestroy(ev);
+        if (evP1) cudaEventDestroy(evP1);
+        if (evDone) cudaEventDestroy(evDone);
+        if (cstream) cudaStreamDestroy(cstream);
+    }
 };
 
 struct GenParams {
@@ -98,12 +112,13 @@ __global__ void k_fill_g3d(const cd* __restrict__ gin, cd* __restrict__ gout, co
     }
 
 // all-to-all of equal contiguous blocks (grouped ncclSend/ncclRecv over NVLink)
-int all_to_all(Op3D* op, const cd* send, cd* recv, long blk_elems) {
+int all_to_all(Op3D* op, const cd* send, cd* recv, long blk_elems, cudaStream_t on = nullptr) {
+    if (!on) on = op->stream;
     ncclResult_t r = ncclGroupStart();
     for (int q = 0; q < op->P && r == ncclSuccess; ++q) {
-        r = ncclSend(send + (long)q * blk_elems, (size_t)blk_elems * 2, ncclDouble, q, op->comm, op->stream);
+        r = ncclSend(send + (long)q * blk_elems, (size_t)blk_elems * 2, ncclDouble, q, op->comm, on);
         if (r == ncclSuccess)
-            r = ncclRecv(recv + (long)q * blk_elems, (size_t)blk_elems * 2, ncclDouble, q, op->comm, op->stream);
+            r = ncclRecv(recv + (long)q * blk_elems, (size_t)blk_elems * 2, ncclDouble, q, op->comm, on);
     }
     ncclResult_t r2 = ncclGroupEnd();
     if (r == ncclSuccess) r = r2;
@@ -116,78 +131,95 @@ int all_to_all(Op3D* op, const cd* send, cd* recv, long blk_elems) {
 
 int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     cudaError_t e = cudaSuccess;
-    cudaStream_t s = op->stream;
-    const long n = op->n, m = op->m, l = op->l, me = op->pm, nel = op->nel, lloc = op->lloc;
-    const int nr = op->nr;
+    cudaStream_t s = op->stream, sc = op->cstream;
+    const long n = op->n, m = op->m, l = op->l, me = op->pm, nel = op->nel, lloc = op->lloc, nelc = op->nelc;
+    const int nr = op->nr, Cx = op->Cx, P = op->P;
     const bool full = (mode == LS_APPLY_FASTCONVOLUTION);
-    const long blk = nel * m * lloc;                 // elements exchanged with each peer
-    int shift = 0;
-    while ((1L << shift) < nel) ++shift;
-    // P1: x lines (j, p_loc): in b[n*line + i]; slot sx -> block sx/nel, A1[(sx/nel)*blk + nel*line + sx%nel]
+    const long blk = nelc * m * lloc;                // elements exchanged with each peer per chunk
+    const long cstride = (long)P * blk;              // one chunk of the exchange buffers (= nelc*m*l)
+    int shc = 0, shr = 0;
+    while ((1L << shc) < nelc) ++shc;
+    while ((1L << shr) < nel) ++shr;
+    // P1: x lines (j, p_loc): in b[n*line + i]; slot sx -> rank q = sx/nel, chunk c = (sx%nel)/nelc:
+    //     A1[c*cstride + q*blk + nelc*line + sx%nelc]
     {
-        LineAddr la{1L << 40, n, 0, 1, nel, 0, 1};
-        la.split_shift = shift; la.split_stride = blk; la.nr = nr;
+        LineAddr la{1L << 40, n, 0, 1, nelc, 0, 1};
+        la.split_shift = shc; la.split_stride = cstride; la.split2_shift = shr; la.split2_stride = blk; la.nr = nr;
         op->phase_begin(0);
 #define C1(N) launch_fwd<N, false>(s, m * lloc, b, full ? op->d_nu : nullptr, op->d_A1, op->d_TABn, la)
         LS3_DISPATCH(n, C1);
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
-    const cd* a1t = op->d_A1;
-    if (op->P > 1) {
-        op->phase_begin(5);
-        int rc = all_to_all(op, op->d_A1, op->d_A1T, blk);
-        op->phase_end();
-        if (rc) return rc;
-        a1t = op->d_A1T;
+    if (P > 1) {      // inbound transposes, chunk by chunk, on the exchange stream
+        LS_CUDA_TRY(cudaEventRecord(op->evP1, s));
+        LS_CUDA_TRY(cudaStreamWaitEvent(sc, op->evP1, 0));
+        for (int c = 0; c < Cx; ++c) {
+            op->phase_begin(5, sc);
+            int rc = all_to_all(op, op->d_A1 + c * cstride, op->d_A1T + c * cstride, blk, sc);
+            op->phase_end(sc);
+            if (rc) return rc;
+            LS_CUDA_TRY(cudaEventRecord(op->evIn[c], sc));
+        }
     }
-    cd* c1t = (op->P > 1) ? op->d_A1T : op->d_A1;
-    // P2: y lines (sxl, p): in A1T[sxl + nel*m*p + nel*j]; out A2[sxl + nel*me*p + nel*sy]
+    static int variant = -1;
+    if (variant < 0) { const char* ev = getenv("LS_P3_VARIANT"); variant = ev ? atoi(ev) : 1; }   // 1: spectrum chunks staged by TMA bulk copies, 0: direct loads
+    for (int c = 0; c < Cx; ++c) {
+        const cd* a1t = (P > 1 ? op->d_A1T : op->d_A1) + c * cstride;     // chunk c re-slabbed: nelc x m x l
+        cd* c1t = (P > 1 ? op->d_A1T : op->d_A1) + c * cstride;
+        const cd* Gc = op->d_G + (long)c * nelc * me * op->pl;
+        if (P > 1) LS_CUDA_TRY(cudaStreamWaitEvent(s, op->evIn[c], 0));
+        // P2: y lines (sxc, p): in A1T[sxc + nelc*m*p + nelc*j]; out A2[sxc + nelc*me*p + nelc*sy]
+        {
+            LineAddr la{nelc, 1, nelc * m, nelc, 1, nelc * me, nelc};
+            la.nr = nr;
+            op->phase_begin(1);
+#define C2(N) launch_fwd<N, true>(s, nelc * l, a1t, nullptr, op->d_A2, op->d_TABm, la)
+            LS3_DISPATCH(m, C2);
+            op->phase_end(); op->launches++;
+            LS_CUDA_TRY(e);
+        }
+        // P3: z lines L = sxc + nelc*sy: point p at A2[L + nelc*me*p], in place
+        {
+            LineAddr la{1L << 40, 1, 0, nelc * me, 1, 0, nelc * me};
+            la.nr = nr;
+            op->phase_begin(2);
+#define C3(N) launch_mid<N, true, false>(s, nelc * me, op->d_A2, op->d_A2, Gc, op->d_TABl, la)
+#define C3T(N) launch_mid<N, true, true>(s, nelc * me, op->d_A2, op->d_A2, Gc, op->d_TABl, la)
+#define C3L2(N) launch_mid_lean<N, 2>(s, nelc * me, op->d_A2, op->d_A2, Gc, op->d_TABl, la)
+#define C3L3(N) launch_mid_lean<N, (GeoB<N>::THREADS <= 128 ? 3 : 1)>(s, nelc * me, op->d_A2, op->d_A2, Gc, op->d_TABl, la)
+            if (variant == 1 || nr != 4) { LS3_DISPATCH(l, C3T); } else if (variant == 2) { LS3_DISPATCH(l, C3L2); }
+            else if (variant == 3) { LS3_DISPATCH(l, C3L3); } else { LS3_DISPATCH(l, C3); }
+            op->phase_end(); op->launches++;
+            LS_CUDA_TRY(e);
+        }
+        // P4: inverse y lines (sxc, p): slots at A2[sxc + nelc*me*p + nelc*sy]; out C1T[sxc + nelc*m*p + nelc*j]
+        {
+            LineAddr la{nelc, 1, nelc * me, nelc, 1, nelc * m, nelc};
+            la.nr = nr;
+            op->phase_begin(3);
+#define C4(N) launch_inv<N, true>(s, nelc * l, op->d_A2, nullptr, c1t, op->d_TABm, 1.0, la)
+            LS3_DISPATCH(m, C4);
+            op->phase_end(); op->launches++;
+            LS_CUDA_TRY(e);
+        }
+        if (P > 1) {  // outbound transpose of this chunk (queued behind the inbound ones on the exchange stream)
+            LS_CUDA_TRY(cudaEventRecord(op->evOut[c], s));
+            LS_CUDA_TRY(cudaStreamWaitEvent(sc, op->evOut[c], 0));
+            op->phase_begin(6, sc);
+            int rc = all_to_all(op, op->d_A1T + c * cstride, op->d_A1 + c * cstride, blk, sc);
+            op->phase_end(sc);
+            if (rc) return rc;
+        }
+    }
+    if (P > 1) {
+        LS_CUDA_TRY(cudaEventRecord(op->evDone, sc));
+        LS_CUDA_TRY(cudaStreamWaitEvent(s, op->evDone, 0));
+    }
+    // P5: inverse x lines + combine; slot sx of line (j, p_loc) addressed as in P1
     {
-        LineAddr la{nel, 1, nel * m, nel, 1, nel * me, nel};
-        la.nr = nr;
-        op->phase_begin(1);
-#define C2(N) launch_fwd<N, true>(s, nel * l, a1t, nullptr, op->d_A2, op->d_TABm, la)
-        LS3_DISPATCH(m, C2);
-        op->phase_end(); op->launches++;
-        LS_CUDA_TRY(e);
-    }
-    // P3: z lines L = sxl + nel*sy: point p at A2[L + nel*me*p], in place
-    {
-        LineAddr la{1L << 40, 1, 0, nel * me, 1, 0, nel * me};
-        la.nr = nr;
-        op->phase_begin(2);
-        static int variant = -1;
-        if (variant < 0) { const char* ev = getenv("LS_P3_VARIANT"); variant = ev ? atoi(ev) : 1; }   // 1: spectrum chunks staged by TMA bulk copies (5.96 ms at 256^3), 0: direct loads (7.1 ms)
-#define C3(N) launch_mid<N, true, false>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
-#define C3T(N) launch_mid<N, true, true>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
-#define C3L2(N) launch_mid_lean<N, 2>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
-#define C3L3(N) launch_mid_lean<N, (GeoB<N>::THREADS <= 128 ? 3 : 1)>(s, nel * me, op->d_A2, op->d_A2, op->d_G, op->d_TABl, la)
-        if (variant == 1 || nr != 4) { LS3_DISPATCH(l, C3T); } else if (variant == 2) { LS3_DISPATCH(l, C3L2); }
-        else if (variant == 3) { LS3_DISPATCH(l, C3L3); } else { LS3_DISPATCH(l, C3); }
-        op->phase_end(); op->launches++;
-        LS_CUDA_TRY(e);
-    }
-    // P4: inverse y lines (sxl, p): slots at A2[sxl + nel*me*p + nel*sy]; out C1T[sxl + nel*m*p + nel*j]
-    {
-        LineAddr la{nel, 1, nel * me, nel, 1, nel * m, nel};
-        la.nr = nr;
-        op->phase_begin(3);
-#define C4(N) launch_inv<N, true>(s, nel * l, op->d_A2, nullptr, c1t, op->d_TABm, 1.0, la)
-        LS3_DISPATCH(m, C4);
-        op->phase_end(); op->launches++;
-        LS_CUDA_TRY(e);
-    }
-    if (op->P > 1) {
-        op->phase_begin(6);
-        int rc = all_to_all(op, op->d_A1T, op->d_A1, blk);
-        op->phase_end();
-        if (rc) return rc;
-    }
-    // P5: inverse x lines + combine; slot sx of line (j, p_loc) at A1[(sx/nel)*blk + nel*line + sx%nel]
-    {
-        LineAddr la{1L << 40, nel, 0, 1, n, 0, 1};
-        la.split_shift = shift; la.split_stride = blk; la.nr = nr;
+        LineAddr la{1L << 40, nelc, 0, 1, n, 0, 1};
+        la.split_shift = shc; la.split_stride = cstride; la.split2_shift = shr; la.split2_stride = blk; la.nr = nr;
         op->phase_begin(4);
 #define C5(N) launch_inv<N, false, true>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
         LS3_DISPATCH(n, C5);
@@ -195,6 +227,20 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
         LS_CUDA_TRY(e);
     }
     return LS_OK;
+}
+
+// chunk-major order of the spectrum units: unit (i, sy) of chunk c, i = x-slot group inside the chunk
+__global__ void k_permute_units(const cd* __restrict__ src, cd* __restrict__ dst, long ug, long ugc, long pm, long unit_elems) {
+    // ug = nel/8 x-slot groups per slab row, ugc = nelc/8 per chunk row
+    const long nunits = ug * pm;
+    for (long ud = blockIdx.x; ud < nunits; ud += gridDim.x) {
+        const long c = ud / (ugc * pm), r = ud % (ugc * pm);
+        const long i = r % ugc, sy = r / ugc;
+        const long us = c * ugc + i + ug * sy;
+        const cd* sp = src + us * unit_elems;
+        cd* dp = dst + ud * unit_elems;
+        for (long k = threadIdx.x; k < unit_elems; k += blockDim.x) dp[k] = sp[k];
+    }
 }
 
 __global__ void k_scale3(cd* a, long n, double s) {
@@ -315,6 +361,10 @@ int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_
         LS_CUDA_TRY(e);
     }
     k_scale3<<<148 * 8, 256, 0, s>>>(G2, (long)slab2, 1.0 / (8.0 * (double)n * (double)m * (double)l));
+    if (op->Cx > 1) {   // chunk-major unit order (Z is free by now and has the same size)
+        k_permute_units<<<148 * 16, 256, 0, s>>>(G2, Z, nel2 / 8, nel2 / op->Cx / 8, 2 * m, 2 * 8 * l);
+        std::swap(G2, Z);
+    }
     LS_CUDA_TRY(cudaStreamSynchronize(s));
     op->dfree(Z == G2 ? nullptr : Z);
     op->d_G = G2;
@@ -365,6 +415,15 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
         }
     }
     const bool compact = !(flags & LS_FLAG_PAD4);
+    {   // x-slot chunks (pipelined transposes): default 4 when sharded, LS_OP3D_CHUNKS overrides; chunks keep >= 8 x-slots
+        const char* ev = getenv("LS_OP3D_CHUNKS");
+        int cx = ev ? atoi(ev) : (nranks > 1 ? 4 : 1);
+        if (cx < 1) cx = 1;
+        while (cx & (cx - 1)) cx &= cx - 1;
+        const long nelf = (compact ? 2 : 4) * n / nranks;
+        while (cx > 1 && nelf / cx < 8) cx /= 2;
+        op->Cx = cx;
+    }
     long nel = op->nel;
     const long lloc = op->lloc;
     const size_t Nloc = (size_t)n * m * lloc, NEloc = (size_t)nel * me * le;
@@ -393,7 +452,13 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
         p.eLk_re = cos(L * omega); p.eLk_im = sin(L * omega);
         p.scale = 1.0 / ((double)ne * (double)me * (double)le);
         if (compact) TRY(compact_spectrum3d(op, d_gin, d_fx, d_fy, d_fz, p));
-        else k_fill_g3d<<<148 * 16, 256, 0, op->stream>>>(d_gin, op->d_G, d_fx, d_fy, d_fz, p);
+        else {
+            const long nc4 = nel / op->Cx;       // chunk-major spectrum: chunk c holds the x-slots [c*nc4, (c+1)*nc4) of the slab
+            for (int c = 0; c < op->Cx; ++c) {
+                p.nel = nc4; p.sx0 = (long)rank * nel + c * nc4;
+                k_fill_g3d<<<148 * 16, 256, 0, op->stream>>>(d_gin, op->d_G + (size_t)c * nc4 * me * le, d_fx, d_fy, d_fz, p);
+            }
+        }
         cudaError_t e = cudaStreamSynchronize(op->stream);
         if (e != cudaSuccess) { set_error("spectrum setup failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
         if (d_gin) op->dfree(d_gin);
@@ -401,9 +466,25 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
     }
     op->pn = op->nr * n; op->pm = op->nr * m; op->pl = op->nr * l;
     op->nel = nel = op->pn / nranks;
+    op->nelc = nel / op->Cx;
     TRY(op->dmalloc((void**)&op->d_A1, (size_t)op->pn * m * lloc * sizeof(cd)));
     if (nranks > 1) TRY(op->dmalloc((void**)&op->d_A1T, (size_t)nel * m * l * sizeof(cd)));
-    TRY(op->dmalloc((void**)&op->d_A2, (size_t)nel * op->pm * l * sizeof(cd)));
+    TRY(op->dmalloc((void**)&op->d_A2, (size_t)op->nelc * op->pm * l * sizeof(cd)));
+    if (nranks > 1) {
+        int lo = 0, hi = 0;
+        cudaError_t ce = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* pv = getenv("LS_OP3D_COMM_PRIO");          // 1 (default): exchange stream at the highest priority, so its
+        const bool high = pv ? atoi(pv) != 0 : true;           // copy kernels get SM slots as soon as line-kernel CTAs retire
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&op->cstream, cudaStreamNonBlocking, high ? hi : lo);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&op->evP1, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&op->evDone, cudaEventDisableTiming);
+        for (int c = 0; c < 2 * op->Cx && ce == cudaSuccess; ++c) {
+            cudaEvent_t ev = nullptr;
+            ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (ce == cudaSuccess) (c < op->Cx ? op->evIn : op->evOut).push_back(ev);
+        }
+        if (ce != cudaSuccess) { set_error("exchange stream setup failed: %s", cudaGetErrorString(ce)); delete op; return LS_ERR_CUDA; }
+    }
 #undef TRY
     *out = reinterpret_cast<ls_handle>(op);
     return LS_OK;

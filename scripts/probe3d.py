@@ -28,5 +28,5 @@ for n in sizes:
     ph, cnt = M.profile_read(5)
     print("n=%d create %.1fs  apply %.3f ms -> %.1f applies/s, alg %.0f GB/s (%.1f%% of 6551) phases(ms) %s" % (
         n, t1 - t0, ms, 1e3 / ms, 2360 * N / ms / 1e6, 2360 * N / ms / 1e6 / 6551 * 100,
-        ["%.3f" % (p / max(c, 1)) for p, c in zip(ph, cnt)]), flush=True)
+        ["%.3f" % (p / reps) for p in ph]) + " chunks=%s" % os.environ.get("LS_OP3D_CHUNKS", "1"), flush=True)
     M.destroy()

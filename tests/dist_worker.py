@@ -76,6 +76,18 @@ def main():
     assert np.linalg.norm(y4 - y_ref[a:b_]) / np.linalg.norm(y_ref[a:b_]) <= 1e-12
     assert np.linalg.norm((y4 - y)) / np.linalg.norm(y_ref[a:b_]) <= 1e-13
     M4.destroy()
+    # the default pipelines the transposes over x-slot chunks; one chunk (serial exchange) gives the same bits
+    os.environ["LS_OP3D_CHUNKS"] = "1"
+    uid1 = lsd.broadcast_unique_id(rank)
+    M1 = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid1)
+    del os.environ["LS_OP3D_CHUNKS"]
+    y1 = M1 * np.ascontiguousarray(b[a:b_])
+    assert np.array_equal(y1, y)
+    for _ in range(3):                               # back-to-back applies reuse the exchange buffers and events
+        y = M * np.ascontiguousarray(y)
+        y1 = M1 * np.ascontiguousarray(y1)
+    assert np.array_equal(y1, y)
+    M1.destroy()
 
     # sharded GMRES (dots all-reduced as scalars) against the oracle history
     X, Y, Z = O.grid3d(x, x, x)
