@@ -23,6 +23,7 @@ rng = np.random.default_rng(4321 + rank)
 b = rng.standard_normal(b_ - a) + 1j * rng.standard_normal(b_ - a)
 db = ls.DeviceBuffer.from_host(b); dy = ls.DeviceBuffer(b.nbytes)
 ref = None
+best = (1e9, 1)
 for cx in chunks:
     os.environ["LS_OP3D_CHUNKS"] = str(cx)
     uid = lsd.broadcast_unique_id(rank)
@@ -51,6 +52,9 @@ for cx in chunks:
         per = [p / reps for p in ph]
         print("P=%d n=%d chunks=%d apply %.3f ms (max over ranks) -> %.1f applies/s; compute %.3f a2a %.3f+%.3f phases %s same_bits=%s" % (
             world, n, cnt[1] // reps, float(t[0]), 1e3 / float(t[0]), sum(per[:5]), per[5], per[6], ["%.3f" % p for p in per], same), flush=True)
+    best = min(best, (float(t[0]), cx))
     M.destroy()
+if rank == 0 and os.environ.get("LS_PROBE_BEST"):
+    open(os.environ["LS_PROBE_BEST"], "w").write(str(best[1]))
 dist.barrier()
 dist.destroy_process_group()

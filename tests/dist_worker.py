@@ -76,8 +76,8 @@ def main():
     assert np.linalg.norm(y4 - y_ref[a:b_]) / np.linalg.norm(y_ref[a:b_]) <= 1e-12
     assert np.linalg.norm((y4 - y)) / np.linalg.norm(y_ref[a:b_]) <= 1e-13
     M4.destroy()
-    # the default pipelines the transposes over x-slot chunks; one chunk (serial exchange) gives the same bits
-    os.environ["LS_OP3D_CHUNKS"] = "1"
+    # large slabs pipeline their transposes over x-slot chunks (on a second stream); forced here: same bits
+    os.environ["LS_OP3D_CHUNKS"] = "4"
     uid1 = lsd.broadcast_unique_id(rank)
     M1 = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid1)
     del os.environ["LS_OP3D_CHUNKS"]
