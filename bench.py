@@ -453,7 +453,7 @@ def main():
                     "d2h_bytes_per_step": 16 * N, "steps": e2e_steps, "api": "fastconvolution(FastM, b) on pinned host arrays"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: 4x forward FFT, spectrum multiply, inverse FFT per padded row)",
+            "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: per padded row, 2 x (forward FFT, spectrum multiply, inverse FFT), accumulated)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_model": "SURVEY.md 8(d), literal pruned-4x pass structure (frac > 1: the implemented 2x-padded pass needs a third of these bytes)",
                          "implemented_bytes_per_launch": impl_bytes_p2, "implemented_achieved": impl_bytes_p2 / (p2_ms * 1e-3) / 1e9,

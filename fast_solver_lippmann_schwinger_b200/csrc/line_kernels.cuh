@@ -633,7 +633,10 @@ k_mid_fused_dual(const cd* in, cd* out, const cd* __restrict__ G, const cd* __re
 // in  : line L slot s at in[L*in_ls + s*in_es]
 // out : line L point j at out[L*out_ls + j*out_es];  if bsrc: out = bsrc + scale*result
 // PF: contiguous lines only - pull the next slot block (and the b values) into L2 one block ahead
-template <int N, bool MODE_B, bool PF = false>
+// PF = 1: next block / b values prefetched into L2.  PF = 2: next block / b values staged in shared memory by
+// cp.async while the current block is transformed (each thread stages exactly the elements it consumes: no
+// extra barrier), which takes two of the kernel's three exposed DRAM latencies off the critical path.
+template <int N, bool MODE_B, int PF = 0>
 __global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS,
                                   ((MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS) <= 128) ? 3 : 1)
 k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __restrict__ TAB, double scale,
@@ -652,17 +655,35 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __res
     const long in_base = line_in(la, L), out_base = line_out(la, L);
     cd acc[E];
     const int nr = la.nr, rstep = 4 / la.nr;
+    constexpr int TH = MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
+    cd* stg = sm + LPC * N + EngTab<N>::TW1N + threadIdx.x;      // PF == 2: element e of this thread at stg[TH*e]
 #pragma unroll 1
     for (int rr = 0; rr < nr; ++rr) {
         const int r = rr * rstep;
         cd v[E];
         const cd* p = in + in_base;
+        if (PF == 2 && rr > 0) {
+            cp_async_wait<0>();
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = p[slot_off(la, (long)(rr * N + t + T * e), la.in_es)];
+            for (int e = 0; e < E; ++e) v[e] = stg[TH * e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = p[slot_off(la, (long)(rr * N + t + T * e), la.in_es)];
+        }
         // pull the next block (or, at the end, the b values of the combine) into L2 while this one is transformed
         // (contiguous lines only: measured on B200, prefetching scattered 16-byte pieces costs more L2
         //  requests than the latency it hides - 2-D P3 0.177 -> 0.223 ms, 3-D P5 0.54 -> 0.44 ms)
-        if (!PF) {
+        if (PF == 2) {
+            if (rr + 1 < nr) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) cp_async16(&stg[TH * e], &p[slot_off(la, (long)((rr + 1) * N + t + T * e), la.in_es)]);
+                cp_async_commit();
+            } else if (bsrc != nullptr) {
+#pragma unroll
+                for (int a = 0; a < E; ++a) cp_async16(&stg[TH * a], &bsrc[out_base + (long)(a * T + t) * la.out_es]);
+                cp_async_commit();
+            }
+        } else if (!PF) {
         } else if (rr + 1 < nr) {
             if (!MODE_B && la.in_es == 1 && (t & 7) == 0) {
 #pragma unroll
@@ -681,7 +702,11 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __res
     for (int a = 0; a < E; ++a) {
         long off = out_base + (long)(a * T + t) * la.out_es;
         cd res = cscale(acc[a], scale);
-        if (bsrc != nullptr) res = cadd(res, bsrc[off]);
+        if (bsrc != nullptr) {
+            if (PF == 2 && a == 0) cp_async_wait<0>();
+            const cd bv = (PF == 2) ? stg[TH * a] : bsrc[off];
+            res = make_double2(__fma_rn(acc[a].x, scale, bv.x), __fma_rn(acc[a].y, scale, bv.y));   // one rounding, same bits in every variant
+        }
         out[off] = res;
     }
 }
@@ -721,10 +746,10 @@ inline cudaError_t launch_mid(cudaStream_t s, long nlines, const cd* in, cd* out
     return cudaPeekAtLastError();
 }
 
-template <int N, bool B, bool PF = false>
+template <int N, bool B, int PF = 0>
 inline cudaError_t launch_inv(cudaStream_t s, long nlines, const cd* in, const cd* bsrc, cd* out, const cd* TAB,
                               double scale, const LineAddr& la) {
-    constexpr int smem = Smem<N, B>::fwd_bytes;
+    constexpr int smem = Smem<N, B>::fwd_bytes + (PF == 2 ? Smem<N, B>::LPC * N * (int)sizeof(cd) : 0);
     constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
     static bool attr = false;
     if (!attr) {

@@ -30,7 +30,8 @@ struct Op2D : Op2DBase {
     cd* d_G = nullptr;        // [sx][ry][slot_y] on the pn x pm grid, normalisation folded in
     cd* d_TABn = nullptr; cd* d_TABm = nullptr;   // engine tables (fft_engine.cuh EngTab)
     cd* d_A = nullptr;        // pn x m
-    cd* d_C = nullptr;        // m x pn (line contiguous)
+    cd* d_C = nullptr;        // P2 output: slot sx of column j at C[(sx/cw)*(cw*m) + cw*j + sx%cw]
+    int cw = 1;               // x-slot interleave of C: P3's strided reads then cover whole sectors (default 4: 64-byte runs)
     int apply_dev(const cd* b, cd* y, int mode) override;
 };
 
@@ -85,8 +86,9 @@ template <int N, bool GSM, int MINB, int ASM = 0> int launch_mid_v(Op2D* op) {
         attr = true;
     }
     dim3 grid((unsigned)(op->pn / GeoA<N>::LPC));
-    // line = x slot sx; point j at A[sx + pn*j]; output line contiguous C[j + m*sx]
-    LineAddr la{1L << 40, 1, 0, op->pn, op->m, 0, 1};
+    // line = x slot sx; point j at A[sx + pn*j]; output: cw adjacent x-slots interleaved, C[(sx/cw)*(cw*m) + cw*j + sx%cw]
+    const long cw = op->cw;
+    LineAddr la{cw, 1, cw, op->pn, 1, cw * op->m, cw};
     la.nr = op->nr;
     op->phase_begin(1);
     k_mid_fused<N, false, GSM, MINB, ASM><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
@@ -149,22 +151,33 @@ template <int N> int launch_mid(Op2D* op) {
     if (variant == 3) return launch_mid_v<N, false, 3, 2>(op);
     return launch_mid_v<N, false, 1>(op);
 }
-template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
-    constexpr int smem = Smem<N, false>::fwd_bytes;
+template <int N, int PF> int launch_inv_v(Op2D* op, const cd* bsrc, cd* y, double scale) {
+    constexpr int smem = Smem<N, false>::fwd_bytes + (PF == 2 ? Smem<N, false>::LPC * N * (int)sizeof(cd) : 0);
     static bool attr = false;
     if (!attr) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(k_inv_pruned<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        LS_CUDA_TRY(cudaFuncSetAttribute(k_inv_pruned<N, false, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
-    // line = column j; slot sx at C[j + m*sx]
-    LineAddr la{1L << 40, 1, 0, op->m, op->n, 0, 1};
+    // line = column j; slot sx at C[(sx/cw)*(cw*m) + cw*j + sx%cw]: adjacent lanes read adjacent slots
+    const long cw = op->cw;
+    int cshift = 0;
+    while ((1L << cshift) < cw) ++cshift;
+    LineAddr la{1L << 40, cw, 0, 1, op->n, 0, 1};
+    la.split_shift = cshift; la.split_stride = cw * op->m;
     la.nr = op->nr;
     op->phase_begin(2);
-    k_inv_pruned<N, false><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(op->d_C, bsrc, y, op->d_TABn, scale, la, 0);
+    k_inv_pruned<N, false, PF><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(op->d_C, bsrc, y, op->d_TABn, scale, la, 0);
     op->phase_end();
     op->launches++;
     return LS_OK;
+}
+template <int N> int launch_inv(Op2D* op, const cd* bsrc, cd* y, double scale) {
+    // LS_P3_STAGE: 1 (default) = next slot block and b staged in shared memory by cp.async while the current block is
+    // transformed, 0 = plain loads (2048^2 on B200: 0.131 -> 0.077 ms together with the 4-slot interleave of C)
+    static int stage = -1;
+    if (stage < 0) { const char* e = getenv("LS_P3_STAGE"); stage = e ? atoi(e) : 1; }
+    return stage ? launch_inv_v<N, 2>(op, bsrc, y, scale) : launch_inv_v<N, 0>(op, bsrc, y, scale);
 }
 
 #define LS_DISPATCH_N(N_, CALL)                                       \
@@ -328,6 +341,14 @@ int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
         TRY(compact_spectrum(op, g4s));
     }
     op->pn = op->nr * n; op->pm = op->nr * m;
+    {   // x-slot interleave of the P2 -> P3 intermediate (LS_C_INTERLEAVE = 1 / 2 / 4 / 8, diagnostic)
+        const char* ev = getenv("LS_C_INTERLEAVE");
+        int cw = ev ? atoi(ev) : 4;        // measured at 2048^2: P2 + P3 = 0.326 / 0.313 / 0.304 / 0.31 ms for 1 / 2 / 4 / 8
+        if (cw != 1 && cw != 2 && cw != 4 && cw != 8) cw = 4;
+        const char* pv = getenv("LS_P2_VARIANT");
+        if (op->nr == 4 && pv && atoi(pv) >= 5) cw = 1;      // the 4x-only experiment kernels write plain rows
+        op->cw = cw;
+    }
     TRY(op->dmalloc((void**)&op->d_A, (size_t)op->pn * m * sizeof(cd)));
     TRY(op->dmalloc((void**)&op->d_C, (size_t)op->pn * m * sizeof(cd)));
     TRY(op->dmalloc((void**)&op->d_b, N * sizeof(cd)));

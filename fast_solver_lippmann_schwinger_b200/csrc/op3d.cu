@@ -162,8 +162,9 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
             LS_CUDA_TRY(cudaEventRecord(op->evIn[c], sc));
         }
     }
-    static int variant = -1;
+    static int variant = -1, stage45 = -1;
     if (variant < 0) { const char* ev = getenv("LS_P3_VARIANT"); variant = ev ? atoi(ev) : 1; }   // 1: spectrum chunks staged by TMA bulk copies, 0: direct loads
+    if (stage45 < 0) { const char* ev = getenv("LS_P45_STAGE"); stage45 = ev ? atoi(ev) : 3; }    // bit 0: P5, bit 1: P4 stage their next slot block (and b) in shared memory by cp.async (256^3: 1.94 -> 1.80 ms)
     for (int c = 0; c < Cx; ++c) {
         const cd* a1t = (P > 1 ? op->d_A1T : op->d_A1) + c * cstride;     // chunk c re-slabbed: nelc x m x l
         cd* c1t = (P > 1 ? op->d_A1T : op->d_A1) + c * cstride;
@@ -199,7 +200,8 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
             la.nr = nr;
             op->phase_begin(3);
 #define C4(N) launch_inv<N, true>(s, nelc * l, op->d_A2, nullptr, c1t, op->d_TABm, 1.0, la)
-            LS3_DISPATCH(m, C4);
+#define C4S(N) launch_inv<N, true, 2>(s, nelc * l, op->d_A2, nullptr, c1t, op->d_TABm, 1.0, la)
+            if (stage45 & 2) { LS3_DISPATCH(m, C4S); } else { LS3_DISPATCH(m, C4); }
             op->phase_end(); op->launches++;
             LS_CUDA_TRY(e);
         }
@@ -221,8 +223,9 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
         LineAddr la{1L << 40, nelc, 0, 1, n, 0, 1};
         la.split_shift = shc; la.split_stride = cstride; la.split2_shift = shr; la.split2_stride = blk; la.nr = nr;
         op->phase_begin(4);
-#define C5(N) launch_inv<N, false, true>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
-        LS3_DISPATCH(n, C5);
+#define C5(N) launch_inv<N, false, 1>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
+#define C5S(N) launch_inv<N, false, 2>(s, m * lloc, op->d_A1, full ? b : nullptr, y, op->d_TABn, full ? op->omega * op->omega : 1.0, la)
+        if (stage45 & 1) { LS3_DISPATCH(n, C5S); } else { LS3_DISPATCH(n, C5); }
         op->phase_end(); op->launches++;
         LS_CUDA_TRY(e);
     }
