@@ -18,6 +18,8 @@ import LinearAlgebra: mul!, ldiv!
 const libls = get(ENV, "LS_CUDA_LIB", "libls_cuda.so")
 
 const LS_MEM_HOST, LS_MEM_DEVICE = Cint(0), Cint(1)
+const LS_FLAG_FORCE_GENERIC, LS_FLAG_PAD4 = Cint(1), Cint(2)
+const LS_ORTH = Dict("ModifiedGramSchmidt" => Cint(0), "ClassicalGramSchmidt" => Cint(1), "DGKS" => Cint(2))
 const LS_QUAD = Dict("trapezoidal" => Cint(0), "Greengard_Vico" => Cint(1))
 
 struct LSCudaError <: Exception
@@ -109,6 +111,24 @@ end
 FFTconvolution(M::GPUFastM3D, b::Array{ComplexF64,1}; verbose::Bool=false) = apply!(similar(b), M, b, 1)   # :39-63
 mul!(Y::AbstractVector{ComplexF64}, M::GPUFastM3D, b::AbstractVector{ComplexF64}) = apply!(Y, M, b, 0)
 
+# ---------------------------------------------------- FastM3D slab-decomposed over several GPUs
+# One Julia process per GPU (Distributed.jl / MPI.jl).  Rank 0 calls nccl_unique_id() and broadcasts the
+# 128 bytes; every rank then builds the operator with its z slab of nu (planes [rank*l/P, (rank+1)*l/P))
+# and applies it to its slab of the vectors.  gmres_gpu! on such an operator all-reduces its dot products.
+function nccl_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:ls_nccl_unique_id, libls), Cint, (Ptr{UInt8},), id))
+    return id
+end
+function GPUFastM3DSharded(nu_slab::Vector{Float64}, n, m, l, k, L, Lp, rank::Integer, nranks::Integer,
+                           id::Vector{UInt8}; pad4::Bool=false)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ls_op3d_create_dist, libls), Cint,
+                (Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Ptr{Float64}, Float64, Float64, Float64, Cint, Cint, Ptr{UInt8}, Cint),
+                out, n, m, l, nu_slab, Float64(k), Float64(L), Float64(Lp), rank, nranks, id, pad4 ? LS_FLAG_PAD4 : 0))
+    return GPUFastM3D(Handle(out[]), nu_slab, 4n, 4m, 4l, n, m, l, Float64(k), "Greengard_Vico")
+end
+
 # ---------------------------------------------------------------- sparsifying preconditioner
 struct GPUSparseMatrixCSC
     h::Handle
@@ -153,11 +173,12 @@ host callback.
 """
 function gmres_gpu!(x::Vector{ComplexF64}, A, b::Vector{ComplexF64}; Pl=nothing, abstol=0.0,
                     reltol=sqrt(eps(Float64)), restart=min(20, length(b)), maxiter=length(b), log=false,
-                    initially_zero=false)
+                    initially_zero=false, orth_meth="ModifiedGramSchmidt")
     N = length(b)
     kh = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ls_krylov_create, libls), Cint, (Ref{Ptr{Cvoid}}, Int64), kh, N))
     K = Handle(kh[])
+    check(ccall((:ls_krylov_set_orth, libls), Cint, (Ptr{Cvoid}, Cint), K.ptr, LS_ORTH[orth_meth]))
     hist = zeros(Float64, maxiter); niter = Ref{Int64}(0); conv = Ref{Cint}(0); mv = Ref{Int64}(0)
     cb = C_NULL; as = C_NULL
     if Pl !== nothing
@@ -177,7 +198,7 @@ function gmres_gpu!(x::Vector{ComplexF64}, A, b::Vector{ComplexF64}; Pl=nothing,
     return log ? (x, (resnorm=hist[1:niter[]], iters=niter[], isconverged=conv[] != 0, mvps=mv[])) : x
 end
 
-export GPUFastM, GPUFastM3D, GPUSparsifyingPreconditioner, GPUSparseMatrixCSC, fastconvolution, FFTconvolution,
+export GPUFastM, GPUFastM3D, GPUFastM3DSharded, nccl_unique_id, GPUSparsifyingPreconditioner, GPUSparseMatrixCSC, fastconvolution, FFTconvolution,
        gmres_gpu!, cscmv!, set_device
 
 end # module

@@ -86,3 +86,49 @@ def test_spm_argument_validation(built_lib):
     rc = L.ls_spm_create(C.byref(h), 2, 2, colptr.ctypes.data_as(C.c_void_p), rowval.ctypes.data_as(C.c_void_p),
                          nz.ctypes.data_as(C.c_void_p))
     assert rc == -1 and b"out of range" in L.ls_last_error()
+
+
+def _split_top_level(s):
+    """Split a comma-separated list, ignoring commas nested in (), {} or []."""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_binding_matches_the_header():
+    """julia/LSCuda.jl cannot be executed here (no Julia in the image): check statically that every ccall names a
+    function declared in include/ls_cuda.h and passes as many arguments as the C prototype takes."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ls_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    protos = {}
+    for m in re.finditer(r"\b(ls_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(_split_top_level(args))
+    jl = open(os.path.join(root, "julia", "LSCuda.jl")).read()
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(\w+),\s*libls\),\s*\w+,\s*\(", jl):
+        name = m.group(1)
+        i, depth = m.end(), 1
+        while depth:                      # the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(jl[i], 0)
+            i += 1
+        types = jl[m.end():i - 1].strip().rstrip(",")
+        nargs = 0 if not types else len(_split_top_level(types))
+        assert name in protos, "LSCuda.jl calls %s, which include/ls_cuda.h does not declare" % name
+        assert nargs == protos[name], "%s: LSCuda.jl passes %d arguments, the header declares %d" % (name, nargs, protos[name])
+        seen += 1
+    assert seen >= 10
