@@ -149,8 +149,7 @@ def run_reference(args, rank, world):
 
 def workload_config(n):
     return {"workload": "2-D Greengard_Vico LS operator apply, grid %dx%d (padded %dx%d), k=2pi/(10h), "
-                        "Gaussian-bump contrast (examples/example.jl:48), rng(1234) complex input; evaluated with 2x padding on the "
-                        "kernel restricted to the needed lags (same operator to 1e-16)" % (n, n, 4 * n, 4 * n),
+                        "Gaussian-bump contrast (examples/example.jl:48), rng(1234) complex input" % (n, n, 4 * n, 4 * n),
             "grid": [n, n], "padded": [4 * n, 4 * n], "quadRule": "Greengard_Vico", "points_per_wavelength": 10,
             "element": "complex128 (two f64)",
             "l2_policy": "inputs larger than L2 (per apply: spectrum %.2f GB + two intermediates of %.2f GB + vectors %.2f GB = %.2f GB > 126 MB)" % (
@@ -453,13 +452,15 @@ def main():
                     "d2h_bytes_per_step": 16 * N, "steps": e2e_steps, "api": "fastconvolution(FastM, b) on pinned host arrays"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "evaluation": "pruned FFTs with 2x padding on the kernel restricted to the lags the cropped apply touches "
+                          "(same operator as the reference's 4x-padded evaluation to 1e-16; LS_FLAG_PAD4 keeps the literal one)",
             "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: per padded row, 2 x (forward FFT, spectrum multiply, inverse FFT), accumulated)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_model": "SURVEY.md 8(d), literal pruned-4x pass structure (frac > 1: the implemented 2x-padded pass needs a third of these bytes)",
                          "implemented_bytes_per_launch": impl_bytes_p2, "implemented_achieved": impl_bytes_p2 / (p2_ms * 1e-3) / 1e9,
                          "implemented_frac": impl_bytes_p2 / (p2_ms * 1e-3) / 1e9 / peak,
-                         "traffic": (0.4027e9 + 0.1140e9) if n == 2048 else None,
-                         "traffic_source": "ncu --set full r1_g at 2048^2: dram read 0.403 GB + write 0.114 GB per launch (profiles/r1_g_notes.md)",
+                         "traffic": (0.4027e9 + 0.1126e9) if n == 2048 else None,
+                         "traffic_source": "ncu --set full r1_j at 2048^2: dram read 0.403 GB + write 0.113 GB per launch (profiles/r1_j_2d_2048_kernel0.txt)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_p2, "launch_ms": p2_ms},
             "apply_roofline": {"survey_bytes_per_apply": 568.0 * N, "survey_achieved": 568.0 * N / (ms / args.steps * 1e-3) / 1e9,
                                "survey_frac": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak,
