@@ -17,6 +17,7 @@
 #include "ls_common.cuh"
 #include "op2d_base.cuh"
 #include "line_kernels.cuh"
+#include "line_kernels_experiments.cuh"
 
 using namespace ls;
 using namespace lsk;

@@ -19,6 +19,7 @@
 // All-to-all volume per rank and direction: 16*nr*N*(P-1)/P^2 bytes.
 #include "ls_common.cuh"
 #include "line_kernels.cuh"
+#include "line_kernels_experiments.cuh"
 #include "dist.cuh"
 #include "gv_spectrum.cuh"
 
