@@ -88,6 +88,7 @@ def lib():
         "ls_op3d_create_dist": (ci, [C.POINTER(vp), i64, i64, i64, vp, dbl, dbl, dbl, ci, ci, vp, ci]),
         "ls_op_size": (ci, [vp, C.POINTER(i64)]),
         "ls_spm_create": (ci, [C.POINTER(vp), i64, i64, vp, vp, vp]),
+        "ls_spm_create_dist": (ci, [C.POINTER(vp), vp, i64, i64, vp, vp, vp]),
         "ls_spm_mv": (ci, [vp, CDouble, vp, CDouble, vp, ci]),
         "ls_spm_info": (ci, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(ci), C.POINTER(ci)]),
         "ls_krylov_create": (ci, [C.POINTER(vp), i64]),

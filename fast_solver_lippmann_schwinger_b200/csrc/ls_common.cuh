@@ -58,6 +58,8 @@ struct HandleBase {
 
     // sharded operators expose their communicator so that Krylov reductions can all-reduce on it
     virtual ncclComm_t nccl_comm() const { return nullptr; }
+    virtual int dist_rank() const { return 0; }
+    virtual int dist_size() const { return 1; }
 
     // optional per-phase CUDA-event profiling (bench roofline of the dominant kernel)
     bool profiling = false;

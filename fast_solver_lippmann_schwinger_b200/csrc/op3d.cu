@@ -53,6 +53,8 @@ struct Op3D : HandleBase {
     int64_t op_size() const override { return n * m * lloc; }
     int apply_dev(const cd* b, cd* y, int mode) override;
     ncclComm_t nccl_comm() const override { return comm; }
+    int dist_rank() const override { return rank; }
+    int dist_size() const override { return P; }
     ~Op3D() override {
         if (comm) ncclCommDestroy(comm);
         for (auto ev : evIn) cudaEventDestroy(ev);

@@ -92,9 +92,29 @@ k_spmv_stencil(const unsigned char* __restrict__ cls, const int* __restrict__ cl
     }
 }
 
-int SpM::mv_dev(cd alpha, const cd* x, cd beta, cd* y, cudaStream_t s) {
+int SpM::mv_dev(cd alpha, const cd* xin, cd beta, cd* y, cudaStream_t s) {
     const int use_beta = (beta.x != 0.0 || beta.y != 0.0) ? 1 : 0;
     const int th = 256;
+    const cd* x = xin;
+    if (halo > 0) {
+        // sharded row slab: x is this rank's slab; the first / last `halo` entries travel to the z-neighbours
+        if (comm != nullptr) {
+            ncclResult_t r = ncclGroupStart();
+            if (rank > 0 && r == ncclSuccess) {
+                r = ncclSend(xin, (size_t)halo * 2, ncclDouble, rank - 1, comm, s);
+                if (r == ncclSuccess) r = ncclRecv(d_xext, (size_t)halo * 2, ncclDouble, rank - 1, comm, s);
+            }
+            if (rank < P - 1 && r == ncclSuccess) {
+                r = ncclSend(xin + (nrows - halo), (size_t)halo * 2, ncclDouble, rank + 1, comm, s);
+                if (r == ncclSuccess) r = ncclRecv(d_xext + halo + nrows, (size_t)halo * 2, ncclDouble, rank + 1, comm, s);
+            }
+            ncclResult_t r2 = ncclGroupEnd();
+            if (r == ncclSuccess) r = r2;
+            if (r != ncclSuccess) { set_error("SpMV halo exchange failed: %s", ncclGetErrorString(r)); return LS_ERR_NCCL; }
+        }
+        LS_CUDA_TRY(cudaMemcpyAsync(d_xext + halo, xin, (size_t)nrows * sizeof(cd), cudaMemcpyDeviceToDevice, s));
+        x = d_xext;
+    }
     if (format == SPM_FORMAT_STENCIL) {
         const size_t smem = (size_t)nent * (sizeof(cd) + sizeof(int)) + (size_t)(ncls + 1) * sizeof(int);
         long blocks = std::min<long>((nrows + th - 1) / th, 148L * 32);
@@ -187,8 +207,8 @@ bool detect_stencil_classes(long nrows, const std::vector<int>& rowptr, const st
 
 extern "C" {
 
-int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* colptr, const int64_t* rowval,
-                  const ls_cdouble* nzval) {
+static int spm_build(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* colptr, const int64_t* rowval,
+                     const ls_cdouble* nzval, bool window) {
     LS_REQUIRE(out && colptr && rowval && nzval, LS_ERR_INVALID, "ls_spm_create: null pointer");
     LS_REQUIRE(nrows > 0 && ncols > 0, LS_ERR_INVALID, "ls_spm_create: non-positive size");
     LS_REQUIRE(colptr[0] == 1, LS_ERR_INVALID, "ls_spm_create: colptr must be 1-based (Julia SparseMatrixCSC)");
@@ -231,7 +251,7 @@ int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* c
     std::vector<unsigned char> cls;
     std::vector<int> cls_ptr, cls_off;
     std::vector<cd> cls_val;
-    if (!(force && atoi(force)) && nrows == ncols &&
+    if (!(force && atoi(force)) && (nrows == ncols || window) &&
         detect_stencil_classes(nrows, rowptr, col, val, cls, cls_ptr, cls_off, cls_val) && !cls_off.empty()) {
         A->format = SPM_FORMAT_STENCIL;
         A->ncls = (int)cls_ptr.size() - 1;
@@ -253,6 +273,34 @@ int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* c
     return LS_OK;
 }
 
+int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* colptr, const int64_t* rowval,
+                  const ls_cdouble* nzval) {
+    return spm_build(out, nrows, ncols, colptr, rowval, nzval, false);
+}
+
+int ls_spm_create_dist(ls_handle* out, ls_handle op, int64_t nrows_local, int64_t halo, const int64_t* colptr,
+                       const int64_t* rowval, const ls_cdouble* nzval) {
+    LS_REQUIRE(out && op, LS_ERR_INVALID, "ls_spm_create_dist: null pointer");
+    HandleBase* o = reinterpret_cast<HandleBase*>(op);
+    LS_REQUIRE(o->kind == KIND_OP3D, LS_ERR_INVALID, "ls_spm_create_dist: `op` must be a 3-D operator handle");
+    LS_REQUIRE(nrows_local == o->op_size(), LS_ERR_INVALID,
+               "ls_spm_create_dist: %ld local rows, the operator's slab has %ld", (long)nrows_local, (long)o->op_size());
+    LS_REQUIRE(halo > 0 && halo <= nrows_local, LS_ERR_INVALID,
+               "ls_spm_create_dist: halo %ld must be in [1, local rows] (neighbour slabs only)", (long)halo);
+    int rc = spm_build(out, nrows_local, nrows_local + 2 * halo, colptr, rowval, nzval, true);
+    if (rc) return rc;
+    SpM* A = reinterpret_cast<SpM*>(*out);
+    A->halo = halo;
+    A->rank = o->dist_rank(); A->P = o->dist_size(); A->comm = o->nccl_comm();
+    rc = A->dmalloc((void**)&A->d_xext, (size_t)A->ncols * sizeof(cd));
+    if (rc == LS_OK && cudaMemset(A->d_xext, 0, (size_t)A->ncols * sizeof(cd)) != cudaSuccess) {
+        set_error("ls_spm_create_dist: cudaMemset failed");
+        rc = LS_ERR_CUDA;
+    }
+    if (rc) { delete A; *out = nullptr; return rc; }
+    return LS_OK;
+}
+
 int ls_spm_mv(ls_handle h, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble beta, ls_cdouble* y, int memloc) {
     LS_REQUIRE(h && x && y, LS_ERR_INVALID, "ls_spm_mv: null argument");
     SpM* A = reinterpret_cast<SpM*>(h);
@@ -264,7 +312,7 @@ int ls_spm_mv(ls_handle h, ls_cdouble alpha, const ls_cdouble* x, ls_cdouble bet
         return A->mv_dev(al, reinterpret_cast<const cd*>(x), be, reinterpret_cast<cd*>(y), A->stream);
     }
     LS_REQUIRE(memloc == LS_MEM_HOST, LS_ERR_INVALID, "ls_spm_mv: unknown memloc %d", memloc);
-    LS_CUDA_TRY(cudaMemcpyAsync(A->d_x, x, (size_t)A->ncols * sizeof(cd), cudaMemcpyHostToDevice, A->stream));
+    LS_CUDA_TRY(cudaMemcpyAsync(A->d_x, x, (size_t)A->x_len() * sizeof(cd), cudaMemcpyHostToDevice, A->stream));
     if (be.x != 0.0 || be.y != 0.0)
         LS_CUDA_TRY(cudaMemcpyAsync(A->d_y, y, (size_t)A->nrows * sizeof(cd), cudaMemcpyHostToDevice, A->stream));
     int rc = A->mv_dev(al, A->d_x, be, A->d_y, A->stream);

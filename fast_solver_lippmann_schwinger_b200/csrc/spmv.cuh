@@ -21,6 +21,14 @@ struct SpM : HandleBase {
     int* d_cls_off = nullptr;
     cd* d_cls_val = nullptr;
     cd* d_x = nullptr; cd* d_y = nullptr;   // staging for host-pointer calls
+    // row slab of a matrix sharded like the 3-D operator (ls_spm_create_dist): columns are stored relative to the
+    // window [row0 - halo, row0 + nrows + halo); every mv gathers the two halo pieces of x from the z-neighbours
+    // (grouped ncclSend/ncclRecv on the operator's communicator, borrowed) into d_xext = [halo | local x | halo].
+    long halo = 0;
+    int rank = 0, P = 1;
+    ncclComm_t comm = nullptr;
+    cd* d_xext = nullptr;
+    long x_len() const { return halo > 0 ? nrows : ncols; }      // length of the caller's x
     // y <- alpha*A*x + beta*y on device pointers, enqueued on stream s
     int mv_dev(cd alpha, const cd* x, cd beta, cd* y, cudaStream_t s);
 };

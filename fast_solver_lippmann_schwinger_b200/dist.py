@@ -97,3 +97,78 @@ class FastM3DSharded(_Handle):
     __mul__ = FastM3D.__mul__
     __matmul__ = FastM3D.__mul__
     mul_ = FastM3D.mul_
+
+
+def matrix_halo(A):
+    """Half bandwidth max|row - col| of a sparse matrix: the halo (in vector entries) a row slab needs from each
+    z-neighbour.  For the 27-point sparsifier on an n x m x l grid this is n*m + n + 1."""
+    coo = A.tocoo()
+    return int(np.max(np.abs(coo.row.astype(np.int64) - coo.col.astype(np.int64)))) if coo.nnz else 1
+
+
+def local_block_csc(A, a, b, halo):
+    """Rows [a, b) of the global N x N matrix A with the columns re-based to the window [a - halo, b + halo):
+    a (b-a) x (b-a+2*halo) scipy CSC matrix; window columns outside [0, N) are empty."""
+    import scipy.sparse as sp
+    N = A.shape[1]
+    rows = A.tocsr()[a:b, :]
+    lo, hi = max(a - halo, 0), min(b + halo, N)
+    if rows[:, :lo].nnz or rows[:, hi:].nnz:
+        raise ValueError("rows [%d, %d) reach beyond the halo %d" % (a, b, halo))
+    mid = rows[:, lo:hi].tocsc()
+    left = sp.csc_matrix((b - a, lo - (a - halo)), dtype=mid.dtype)
+    right = sp.csc_matrix((b - a, (b + halo) - hi), dtype=mid.dtype)
+    blk = sp.hstack([left, mid, right], format="csc")
+    blk.sort_indices()
+    return blk
+
+
+class GPUSparseMatrixCSCSharded(_Handle):
+    """Row slab of the sparsifying matrix As living next to a FastM3DSharded operator (same z-slab decomposition).
+    `A` is the global scipy matrix (every rank holds it on the host, as the reference's setup does) or an already
+    extracted local block (then pass halo).  mv / * take and return this rank's slab; collective over the ranks."""
+
+    def __init__(self, A, op, halo=None, is_local_block=False):
+        super().__init__()
+        from .krylov import _julia_csc
+        a, b = vector_range(op.n, op.m, op.l, op.rank, op.nranks)
+        if is_local_block:
+            if halo is None:
+                raise ValueError("a local block needs its halo")
+            blk = A
+        else:
+            halo = matrix_halo(A) if halo is None else int(halo)
+            blk = local_block_csc(A, a, b, halo)
+        self.halo = int(halo)
+        nrows, ncols, colptr, rowval, nzval = _julia_csc(blk)
+        if nrows != b - a or ncols != nrows + 2 * self.halo:
+            raise ValueError("DimensionMismatch: local block is %d x %d, expected %d x %d" % (nrows, ncols, b - a, b - a + 2 * self.halo))
+        self.shape = (nrows, nrows)
+        self.nnz = int(colptr[-1] - 1)
+        self._op = op                         # the operator (and its communicator) must outlive the matrix
+        check(lib().ls_spm_create_dist(C.byref(self._h), op.handle, nrows, self.halo, ptr(colptr), ptr(rowval), ptr(nzval)))
+        fmt, ncl = C.c_int(), C.c_int()
+        check(lib().ls_spm_info(self.handle, None, None, None, C.byref(fmt), C.byref(ncl)))
+        self.format = "stencil" if fmt.value == 1 else "csr"
+        self.nclasses = int(ncl.value)
+
+    def mv(self, x, y=None, alpha=1.0, beta=0.0):
+        """y <- alpha*A*x + beta*y on this rank's slabs (device buffers or contiguous complex128 arrays)."""
+        from ._lib import CDouble
+        if isinstance(x, DeviceBuffer):
+            if not isinstance(y, DeviceBuffer):
+                raise TypeError("device x needs a device y")
+            check(lib().ls_spm_mv(self.handle, CDouble.of(alpha), ptr(x), CDouble.of(beta), ptr(y), _lib.MEM_DEVICE))
+            return y
+        x = _as_c128(x, self.shape[1], "x")
+        if y is None:
+            if beta != 0:
+                raise ValueError("beta != 0 needs y")
+            y = np.empty(self.shape[0], dtype=np.complex128)
+        check(lib().ls_spm_mv(self.handle, CDouble.of(alpha), ptr(x), CDouble.of(beta), ptr(y), _lib.MEM_HOST))
+        return y
+
+    def __mul__(self, x):
+        return self.mv(x)
+
+    __matmul__ = __mul__

@@ -116,6 +116,15 @@ int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int
  * to CSR/int32 on the device.                                                              */
 int ls_spm_create(ls_handle* out, int64_t nrows, int64_t ncols, const int64_t* colptr,
                   const int64_t* rowval, const ls_cdouble* nzval);
+/* Row slab of As for the slab-decomposed 3-D operator `op` (ls_op3d_create_dist; SURVEY.md 8(e): the 27-point
+ * sparsifier of SparsifyingMatrix3D.jl:1410-1653 couples a row only to rows within n*m + n + 1, i.e. to the
+ * neighbouring z planes).  The CSC arrays (1-based, as ls_spm_create) hold the block
+ * A[row0 : row0 + nrows_local, row0 - halo : row0 + nrows_local + halo), nrows_local + 2*halo columns, columns
+ * outside the global matrix empty; row0 = first row of this rank's slab, halo <= nrows_local and equal on every
+ * rank.  ls_spm_mv then takes x and y as this rank's slabs and fetches the halo of x from the z-neighbours on
+ * the operator's communicator (collective: every rank calls it).  `op` must outlive the matrix.            */
+int ls_spm_create_dist(ls_handle* out, ls_handle op, int64_t nrows_local, int64_t halo, const int64_t* colptr,
+                       const int64_t* rowval, const ls_cdouble* nzval);
 /* y <- alpha*A*x + beta*y : `M.As*b` (preconditioner.jl:138,142,159,163) is alpha=1, beta=0;
  * same meaning as SparseBLAS.cscmv!('N', alpha, "GXXF", A, x, beta, y), sparseblas.jl:14-25.
  * x and y must not alias.                                                                  */

@@ -89,6 +89,24 @@ def main():
     assert np.array_equal(y1, y)
     M1.destroy()
 
+    # sharded SpMV of a 27-point sparsifier-like matrix: halo planes of x come from the z-neighbours
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util_sparse import stencil27
+    xg = rng.standard_normal(n ** 3) + 1j * rng.standard_normal(n ** 3)
+    for classes in (True, False):
+        A = stencil27(n, n, l, seed=21, classes=classes)
+        As = lsd.GPUSparseMatrixCSCSharded(A, M)
+        assert As.format == ("stencil" if classes else "csr") and As.halo == n * n + n + 1
+        ys = As * np.ascontiguousarray(xg[a:b_])
+        yr = (A @ xg)[a:b_]
+        e = np.linalg.norm(ys - yr) / np.linalg.norm(yr)
+        assert e <= 1e-14, e
+        dxs, dys = ls.DeviceBuffer.from_host(np.ascontiguousarray(xg[a:b_])), ls.DeviceBuffer(16 * (b_ - a))
+        As.mv(dxs, dys, alpha=2.0)
+        As.sync()
+        assert np.linalg.norm(dys.to_host() - 2.0 * yr) / np.linalg.norm(yr) <= 1e-14
+        As.destroy()
+
     # sharded GMRES (dots all-reduced as scalars) against the oracle history
     X, Y, Z = O.grid3d(x, x, x)
     u_inc = np.exp(1j * k * X)

@@ -4,10 +4,13 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "dist_worker.py")
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def _torchrun(nproc, args, port, timeout=600):
@@ -39,6 +42,32 @@ def _gpu_count():
         return sum(1 for line in out.splitlines() if line.startswith("GPU "))
     except Exception:
         return 0
+
+
+def test_row_slab_blocks_of_the_sparsifier():
+    """Host logic of the sharded SpMV: every rank's windowed row block, applied to [halo | slab | halo], gives its
+    slab of A @ x; the 27-point structure needs exactly n*m + n + 1 entries from each z-neighbour."""
+    from util_sparse import stencil27
+    from fast_solver_lippmann_schwinger_b200 import dist as lsd
+    n, m, l, P = 6, 5, 8, 4
+    A = stencil27(n, m, l, seed=3)
+    assert lsd.matrix_halo(A) == n * m + n + 1
+    N = n * m * l
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    y = A @ x
+    H = lsd.matrix_halo(A)
+    for r in range(P):
+        a, b = lsd.vector_range(n, m, l, r, P)
+        assert H <= b - a
+        blk = lsd.local_block_csc(A, a, b, H)
+        assert blk.shape == (b - a, b - a + 2 * H)
+        xext = np.zeros(b - a + 2 * H, complex)
+        lo, hi = max(a - H, 0), min(b + H, N)
+        xext[lo - (a - H): lo - (a - H) + hi - lo] = x[lo:hi]
+        assert np.allclose(blk @ xext, y[a:b], rtol=0, atol=1e-13)
+    with pytest.raises(ValueError):
+        lsd.local_block_csc(A, 0, n * m, 3)          # halo too small for the stencil
 
 
 @pytest.mark.gpu
