@@ -129,6 +129,19 @@ function GPUFastM3DSharded(nu_slab::Vector{Float64}, n, m, l, k, L, Lp, rank::In
     return GPUFastM3D(Handle(out[]), nu_slab, 4n, 4m, 4l, n, m, l, Float64(k), "Greengard_Vico")
 end
 
+"""
+Row slab of the sparsifier next to a sharded operator: `Ablk` is `As[rows, (first(rows)-halo):(last(rows)+halo)]`
+(columns outside the matrix empty), `rows` the rank's slab of `M`.  `As_sh * x` is collective: the halo of x
+comes from the two z-neighbours.
+"""
+function GPUSparseMatrixCSCSharded(Ablk::SparseMatrixCSC{ComplexF64,Int64}, M::GPUFastM3D, halo::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ls_spm_create_dist, libls), Cint,
+                (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}),
+                out, M.h.ptr, Ablk.m, halo, Ablk.colptr, Ablk.rowval, Ablk.nzval))
+    return GPUSparseMatrixCSC(Handle(out[]), Ablk.m, Ablk.m)
+end
+
 # ---------------------------------------------------------------- sparsifying preconditioner
 struct GPUSparseMatrixCSC
     h::Handle
