@@ -461,6 +461,132 @@ def buildSparseAG(k, X, Y, D0, n, m, strict=True, _cache=None):
     return _assemble(n, m, Indices, ValuesAG)
 
 
+# --------------------------------------------------------------------------------------
+# 3-D sparsifying matrices (SparsifyingMatrix3D.jl) - setup code of examples/example3D.jl:56-61,
+# restated to obtain a realistic 27-point As / Msp for the 3-D SpMV and preconditioned GMRES.
+# --------------------------------------------------------------------------------------
+# Boundary classes in the order entriesSparseA3D pushes them (SparsifyingMatrix3D.jl:1136-1408) and
+# buildSparseA3DConv consumes them (:1410-1653): interior, 6 faces, 12 edges ("vertices" upstream), 8 corners.
+# Per dimension: "lo" = first grid plane (stencil offsets 0,+1), "mid" = interior (-1,0,+1), "hi" = last (-1,0).
+_CLASSES_3D = [
+    ("mid", "mid", "mid"),
+    ("lo", "mid", "mid"), ("hi", "mid", "mid"), ("mid", "lo", "mid"), ("mid", "hi", "mid"),
+    ("mid", "mid", "lo"), ("mid", "mid", "hi"),
+    ("lo", "lo", "mid"), ("hi", "lo", "mid"), ("lo", "hi", "mid"), ("hi", "hi", "mid"),
+    ("lo", "mid", "lo"), ("hi", "mid", "lo"), ("lo", "mid", "hi"), ("hi", "mid", "hi"),
+    ("mid", "lo", "lo"), ("mid", "hi", "lo"), ("mid", "lo", "hi"), ("mid", "hi", "hi"),
+    ("lo", "lo", "lo"), ("hi", "lo", "lo"), ("lo", "hi", "lo"), ("hi", "hi", "lo"),
+    ("lo", "lo", "hi"), ("hi", "lo", "hi"), ("lo", "hi", "hi"), ("hi", "hi", "hi"),
+]
+_OFFS_3D = {"lo": (0, 1), "mid": (-1, 0, 1), "hi": (-1, 0)}
+
+
+def _stencil_offsets_3d(cls, n, m):
+    """Ind_relative[...][:] of SparsifyingMatrix3D.jl:1147-1158 restricted to the class (x fastest)."""
+    cx, cy, cz = cls
+    return np.array([dx + n * dy + n * m * dz for dz in _OFFS_3D[cz] for dy in _OFFS_3D[cy] for dx in _OFFS_3D[cx]],
+                    dtype=np.int64)
+
+
+def _class_centre_3d(cls, n, m, l):
+    """1-based index of the representative point: plane 1 / round(n/2) / n per dimension (changeInd3D, :7-11)."""
+    def coord(c, nn):
+        return 1 if c == "lo" else (nn if c == "hi" else int(round(nn / 2)))     # Julia round: half to even, as Python
+    i, j, p = coord(cls[0], n), coord(cls[1], m), coord(cls[2], l)
+    return (p - 1) * n * m + (j - 1) * n + i
+
+
+def sampleG3D(k, X, Y, Z, indS, fastconv: FastM3D, toeplitz=True):
+    """FastConvolution3D.jl:136-160: row i = FFTconvolution(fastconv, e_{indS[i]}) (1-based indS).
+
+    toeplitz=False runs the applies literally.  toeplitz=True reads the same numbers from the spatial kernel
+    g = ifftn(ifftshift(GFFT)) (the apply is a circular convolution with g on the padded grid, cropped), which is
+    what makes sampling 343 rows affordable; tests/test_oracle.py checks both paths against each other."""
+    indS = np.asarray(indS, dtype=np.int64)
+    N = fastconv.n * fastconv.m * fastconv.l
+    if not toeplitz:
+        G = np.zeros((len(indS), N), dtype=np.complex128)
+        for i, s0 in enumerate(indS):
+            e = np.zeros(N, dtype=np.complex128)
+            e[s0 - 1] = 1.0
+            G[i, :] = FFTconvolution3D(fastconv, e)
+        return G
+    g = getattr(fastconv, "_g_spatial", None)
+    if g is None:
+        g = _ifft(sfft.ifftshift(fastconv.GFFT))
+        object.__setattr__(fastconv, "_g_spatial", g)
+    n, m, l = fastconv.n, fastconv.m, fastconv.l
+    I = np.arange(n)[:, None, None]
+    J = np.arange(m)[None, :, None]
+    P = np.arange(l)[None, None, :]
+    G = np.empty((len(indS), N), dtype=np.complex128)
+    for i, s0 in enumerate(indS - 1):
+        si, sj, sp_ = s0 % n, (s0 // n) % m, s0 // (n * m)
+        G[i, :] = g[(I - si) % fastconv.ne, (J - sj) % fastconv.ne, (P - sp_) % fastconv.le].reshape(-1, order="F")
+    return G
+
+
+def entriesSparseA3D(k, X, Y, Z, fastconv: FastM3D, n, m, l, toeplitz=True):
+    """SparsifyingMatrix3D.jl:1136-1408: per boundary class the last left singular vector of G sampled from the
+    class's stencil points to every other grid point.  Returns (Indices, Entries) like upstream."""
+    N = n * m * l
+    allidx = np.arange(1, N + 1)
+    Indices, Entries = [], []
+    for cls in _CLASSES_3D:
+        rel = _stencil_offsets_3d(cls, n, m)
+        ind = _class_centre_3d(cls, n, m, l) + rel
+        indC = np.setdiff1d(allidx, ind)
+        GS = sampleG3D(k, X, Y, Z, ind, fastconv, toeplitz)[:, indC - 1]
+        U, s, Vh = np.linalg.svd(GS, full_matrices=False)
+        Entries.append(np.conj(U[:, -1]))            # U[:,end]'
+        Indices.append(rel)
+    return Indices, Entries
+
+
+def entriesSparseG3D(k, X, Y, Z, fastconv: FastM3D, n, m, l, toeplitz=True):
+    """SparsifyingMatrix3D.jl:963-1135: G restricted to each class's own stencil (same class order)."""
+    out = []
+    for cls in _CLASSES_3D:
+        ind = _class_centre_3d(cls, n, m, l) + _stencil_offsets_3d(cls, n, m)
+        out.append(sampleG3D(k, X, Y, Z, ind, fastconv, toeplitz)[:, ind - 1])
+    return out
+
+
+def _class_rows_3d(n, m, l):
+    """Row sets Ind[...][:] in the order of buildSparseA3DConv (SparsifyingMatrix3D.jl:1427-1648)."""
+    Ind = np.arange(1, n * m * l + 1, dtype=np.int64).reshape((n, m, l), order="F")
+    sel = {"lo": slice(0, 1), "mid": slice(1, -1), "hi": slice(-1, None)}
+    return [Ind[sel[cx], sel[cy], sel[cz]].reshape(-1, order="F") for cx, cy, cz in _CLASSES_3D]
+
+
+def _assemble_3d(n, m, l, Indices, Values):
+    rows, cols, vals = [], [], []
+    for rset, ind, val in zip(_class_rows_3d(n, m, l), Indices, Values):
+        R, C, V = createIndices(rset, ind, np.asarray(val).reshape(-1))
+        rows.append(R)
+        cols.append(C)
+        vals.append(V)
+    N = n * m * l
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows) - 1, np.concatenate(cols) - 1)), shape=(N, N)).tocsc()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+def buildSparseA3DConv(k, X, Y, Z, fastconv: FastM3D, n, m, l, _cache=None):
+    """SparsifyingMatrix3D.jl:1410-1653 (method = "normal")."""
+    Indices, Values = _cache if _cache is not None else entriesSparseA3D(k, X, Y, Z, fastconv, n, m, l)
+    return _assemble_3d(n, m, l, Indices, Values)
+
+
+def buildSparseAG3DConv(k, X, Y, Z, fastconv: FastM3D, n, m, l, _cache=None):
+    """SparsifyingMatrix3D.jl:1659-1917: rows Values[c] * Entries[c] on the same stencils (As*G truncated)."""
+    Indices, Values = _cache if _cache is not None else entriesSparseA3D(k, X, Y, Z, fastconv, n, m, l)
+    Entries = entriesSparseG3D(k, X, Y, Z, fastconv, n, m, l)
+    ValuesAG = [np.asarray(v).reshape(1, -1) @ e for v, e in zip(Values, Entries)]
+    return _assemble_3d(n, m, l, Indices, ValuesAG)
+
+
 def csc_matvec(A: sp.csc_matrix, x):
     """SparseArrays' ``A*x`` for CSC - the column-scatter loop (== sparseblas.jl:14-25 with
     alpha=1, beta=0).  scipy's csc_matvec runs the same loop in C."""
@@ -552,6 +678,24 @@ def pow2_problem_2d(n, ppw=10.0, nu=nu_gaussian_2d, a=1.0):
     x = -a / 2 + h * np.arange(n)
     k = 2 * np.pi / (ppw * h)
     return x, h, k, buildFastConvolution(x, x, h, k, nu, quadRule="Greengard_Vico")
+
+
+def example_problem_3d(n, l=None, a=1.0, ppw=None, nu=nu_gaussian_3d):
+    """examples/example3D.jl:18-61 on an n x n x l grid (the script ships h = 1/48, x = -a/2:h:a/2-h, i.e. n = l = 48,
+    k = 1/h): operator, As, Msp = As + k^2 AG diag(nu) (:56-61) and the SparsifyingPreconditioner (SuperLU stands in
+    for MKL PARDISO).  ppw overrides k = 1/h with k = 2 pi / (ppw h)."""
+    l = n if l is None else l
+    h = a / n
+    x = -a / 2 + h * np.arange(n)
+    z = -a / 2 * l / n + h * np.arange(l)
+    k = (1.0 / h) if ppw is None else 2 * np.pi / (ppw * h)
+    M = buildFastConvolution3D(x, x, z, h, k, nu)
+    X, Y, Z = grid3d(x, x, z)
+    cache = entriesSparseA3D(k, X, Y, Z, M, n, n, l)
+    As = buildSparseA3DConv(k, X, Y, Z, M, n, n, l, _cache=cache)
+    AG = buildSparseAG3DConv(k, X, Y, Z, M, n, n, l, _cache=cache)
+    Msp = (As + k ** 2 * (AG @ sp.diags(M.nu))).tocsc()
+    return (x, z), h, k, M, As, Msp, SparsifyingPreconditioner(Msp, As)
 
 
 def pow2_problem_3d(n, ppw=10.0, nu=nu_gaussian_3d, a=1.0):

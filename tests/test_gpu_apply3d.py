@@ -179,38 +179,3 @@ def test_x_slot_chunks_give_the_same_apply(chunks, pad4, monkeypatch):
     assert _rel(yc, ref) <= TOL and _rel(Ag * b, ref) <= TOL
     assert np.array_equal(yc, y1)
     assert _rel(ls.FFTconvolution(Ac, b), ls.FFTconvolution(A1, b)) == 0.0
-
-
-@pytest.mark.parametrize("classes", [True, False])
-def test_row_slab_sparse_matrix_on_one_gpu(classes):
-    """ls_spm_create_dist on an unsharded 3-D operator: the windowed row block [halo | rows | halo] without any
-    exchange - stencil-class and CSR storage - against scipy."""
-    import sys, os
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from util_sparse import stencil27
-    import fast_solver_lippmann_schwinger_b200 as ls
-    from fast_solver_lippmann_schwinger_b200 import dist as lsd
-    n = l = 64
-    h = 1.0 / n
-    k = 2 * np.pi / (10 * h)
-    nu = np.zeros(n * n * l)
-    M = lsd.FastM3DSharded(nu, n, n, l, k, 1.8 * n * h, 4.0 * n * h, 0, 1, None)
-    A = stencil27(n, n, l, seed=11, classes=classes)
-    As = lsd.GPUSparseMatrixCSCSharded(A, M)
-    assert As.halo == n * n + n + 1
-    assert As.format == ("stencil" if classes else "csr")
-    if classes:
-        assert As.nclasses == 27
-    rng = np.random.default_rng(9)
-    x = rng.standard_normal(n * n * l) + 1j * rng.standard_normal(n * n * l)
-    ref = A @ x
-    y = As * x
-    assert _rel(y, ref) <= 1e-14
-    y2 = As.mv(x, y=y.copy(), alpha=0.5 - 1j, beta=2.0)
-    assert _rel(y2, (0.5 - 1j) * ref + 2.0 * y) <= 1e-14
-    dx, dy = ls.DeviceBuffer.from_host(x), ls.DeviceBuffer(x.nbytes)
-    As.mv(dx, dy)
-    As.sync()                                     # device-pointer calls are asynchronous on the handle's stream
-    assert _rel(dy.to_host(), ref) <= 1e-14
-    with pytest.raises(ls.LSCudaError):
-        lsd.GPUSparseMatrixCSCSharded(A, M, halo=n * n * l + 1)     # halo larger than the slab

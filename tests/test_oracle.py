@@ -186,3 +186,44 @@ def test_golden_fixtures_reproduce():
     assert _rel(O.FFTconvolution(M, b), g["y_FFTconvolution"]) < 1e-14
     gg = np.load(os.path.join(GOLD, "gmres2d_n64.npz"))
     assert gg["hist_precond"].shape[0] < gg["hist_plain"].shape[0]
+
+
+def test_sparsifier_3d_restatement():
+    """SparsifyingMatrix3D.jl:963-1135, 1136-1408, 1410-1653, 1659-1917 restated (example3D.jl:56-61): structure of As,
+    the literal sampleG3D against the Toeplitz shortcut, far-field suppression and the preconditioner's effect."""
+    from oracle.gmres_is import gmres
+    n, l = 8, 10
+    (x, z), h, k, M, As, Msp, P = O.example_problem_3d(n, l)
+    N = n * n * l
+    X, Y, Z = O.grid3d(x, x, z)
+    # 27 boundary classes: interior 27 entries, faces 18, edges 12, corners 8 (SURVEY a11)
+    assert As.shape == (N, N)
+    assert As.nnz == (n - 2) ** 2 * (l - 2) * 27 + (2 * (n - 2) ** 2 + 4 * (n - 2) * (l - 2)) * 18 \
+        + (8 * (n - 2) + 4 * (l - 2)) * 12 + 64
+    coo = As.tocoo()
+    assert np.max(np.abs(coo.row - coo.col)) == n * n + n + 1                 # half bandwidth nm + n + 1
+    csr = As.tocsr()
+    classes = {(tuple(csr.indices[csr.indptr[r]:csr.indptr[r + 1]] - r), csr.data[csr.indptr[r]:csr.indptr[r + 1]].tobytes())
+               for r in range(N)}
+    assert len(classes) == 27
+    # sampleG3D: applies of unit vectors (FastConvolution3D.jl:136-160) == shifted copies of the spatial kernel
+    ind = np.array([1, n, n * n + 3, N // 2, N])
+    lit = O.sampleG3D(k, X, Y, Z, ind, M, toeplitz=False)
+    assert np.abs(lit - O.sampleG3D(k, X, Y, Z, ind, M)).max() <= 1e-14 * np.abs(lit).max()
+    # each stencil is a unit vector (last left singular vector) ...
+    Indices, Values = O.entriesSparseA3D(k, X, Y, Z, M, n, n, l)
+    assert [len(v) for v in Values] == [27] + [18] * 6 + [12] * 12 + [8] * 8
+    assert all(abs(np.linalg.norm(v) - 1) < 1e-12 for v in Values)
+    # ... chosen so that As*G is (nearly) supported on the stencil: the truncated AG reproduces it
+    G = O.sampleG3D(k, X, Y, Z, np.arange(1, N + 1), M)
+    AsG = As @ G
+    AG = O.buildSparseAG3DConv(k, X, Y, Z, M, n, n, l).toarray()
+    assert np.allclose(AG[AG != 0], AsG[AG != 0], rtol=1e-10, atol=1e-14)       # same numbers on the stencil
+    assert np.linalg.norm(AsG - AG) < 0.25 * np.linalg.norm(AsG)                 # little left outside
+    # the preconditioned solve needs no more iterations and gives the same solution
+    u_inc = np.exp(1j * k * X)
+    rhs = -(M * u_inc - u_inc)
+    u0, h0, c0, _ = gmres(np.zeros(N, complex), lambda v: M * v, rhs)
+    u1, h1, c1, _ = gmres(np.zeros(N, complex), lambda v: M * v, rhs, Pl_ldiv=P.solve)
+    assert c0 and c1 and len(h1) <= len(h0)
+    assert np.linalg.norm(u1 - u0) <= 1e-6 * np.linalg.norm(u0)
