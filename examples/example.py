@@ -7,10 +7,11 @@ high-frequency configuration (10 points per wavelength) instead.
 
     python examples/example.py [--n 201] [--reltol 1.49e-8]
 
-The sparsifying preconditioner of example.jl:64-71 needs the reference's setup code
-(buildSparseA / buildSparseAG, SVDs of sampled Green's functions - out of this repository's
-scope); pass its matrices with --precond file.npz (arrays As_colptr, As_rowval, As_nzval,
-Msp_colptr, Msp_rowval, Msp_nzval in Julia's 1-based CSC layout) to use it.
+The sparsifying preconditioner of example.jl:64-71: `--precond conv` builds As and Mapproxsp with the
+convolution-sampled variants of the reference's setup code (buildSparseAConv / buildSparseAGConv,
+SparsifyingMatrix2D.jl:441-532, 888-966: 61 unit-vector applies on the GPU operator + nine small SVDs);
+`--precond file.npz` takes matrices computed elsewhere (e.g. by the reference's Hankel-sampled buildSparseA),
+arrays As_colptr, As_rowval, As_nzval, Msp_colptr, Msp_rowval, Msp_nzval in Julia's 1-based CSC layout.
 """
 import argparse
 import os
@@ -46,7 +47,17 @@ def main():
     fastconv = ls.FastM(gv_spectrum_2d(n, n, h, k), nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico")
     print("operator on the GPU in %.2f s (n = %d, padded %d)" % (time.time() - t0, n, 4 * n))
     precond = None
-    if args.precond:
+    if args.precond == "conv":
+        import scipy.sparse as sp
+        from fast_solver_lippmann_schwinger_b200 import sparsifier
+        t0 = time.time()
+        cache = sparsifier.entriesSparseAConv(k, X, Y, fastconv, n, n, strict=False)
+        As = sparsifier.buildSparseAConv(k, X, Y, fastconv, n, n, strict=False, _cache=cache)
+        AG = sparsifier.buildSparseAGConv(k, X, Y, fastconv, n, n, strict=False, _cache=cache)
+        Msp = (As + k ** 2 * (AG @ sp.diags(nu))).tocsc()
+        print("As, Mapproxsp from GPU applies in %.2f s" % (time.time() - t0))
+        precond = ls.SparsifyingPreconditioner(Msp, As)
+    elif args.precond:
         import scipy.sparse as sp
         d = np.load(args.precond)
         N = n * n

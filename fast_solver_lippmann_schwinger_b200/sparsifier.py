@@ -1,0 +1,259 @@
+"""Sparsifying matrices built from operator applies.
+
+The reference builds the preconditioner's stencil matrix ``As`` by sampling rows of the discrete
+Green's operator with ``FFTconvolution`` applied to unit vectors and taking, per boundary class, the
+last left singular vector of the far-field block (2-D: sampleGConv FastConvolution.jl:278-306,
+entriesSparseAConv / entriesSparseGConv / buildSparseAGConv / buildSparseAConv
+SparsifyingMatrix2D.jl:104-201, 278-350, 441-532, 888-966; 3-D: sampleG3D FastConvolution3D.jl:136-160,
+entriesSparseG3D / entriesSparseA3D / buildSparseA3DConv / buildSparseAG3DConv
+SparsifyingMatrix3D.jl:963-1135, 1136-1408, 1410-1653, 1659-1917).  Here the applies run on the GPU
+operator (``FastM`` / ``FastM3D``); the 9 / 27 small SVDs stay on the host.
+
+Same names, argument order and return values as upstream.  The stencil vectors are singular vectors and
+therefore defined up to a unit phase: ``Msp^-1 As`` does not depend on it.
+
+Every function takes ``apply=`` (default: ``FFTconvolution`` of this package, i.e. the GPU path); tests
+inject a CPU apply to check the bookkeeping without a device.  Host memory: a class samples
+``len(stencil) x N`` complex numbers (27 N at most: 0.9 GB at 128^3, 7.2 GB at 256^3).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from .operators import FFTconvolution as _gpu_fftconvolution
+
+__all__ = ["createIndices", "sampleGConv", "sampleG3D", "entriesSparseAConv", "entriesSparseGConv",
+           "buildSparseAConv", "buildSparseAGConv", "entriesSparseA3D", "entriesSparseG3D",
+           "buildSparseA3DConv", "buildSparseAG3DConv"]
+
+
+def createIndices(row, col, val):
+    """Functions.jl:7-29: every row gets the same (relative column, value) list.  1-based indices."""
+    row = np.atleast_1d(np.asarray(row, dtype=np.int64))
+    col = np.asarray(col, dtype=np.int64).reshape(-1)
+    val = np.asarray(val, dtype=np.complex128).reshape(-1)
+    if col.shape != val.shape:
+        raise AssertionError("length(col) == length(val)")
+    Row = np.repeat(row, col.size)
+    return Row, np.tile(col, row.size) + Row, np.tile(val, row.size)
+
+
+def _sample_rows(fastconv, N, indS, apply):
+    """Row i = FFTconvolution(fastconv, e_{indS[i]}); indS is 1-based."""
+    apply = _gpu_fftconvolution if apply is None else apply
+    indS = np.asarray(indS, dtype=np.int64).reshape(-1)
+    if indS.min() < 1 or indS.max() > N:
+        raise IndexError("stencil index outside the grid (grid too small for a 3-point stencil?)")
+    G = np.empty((indS.size, N), dtype=np.complex128)
+    e = np.zeros(N, dtype=np.complex128)
+    for i, s0 in enumerate(indS):
+        e[s0 - 1] = 1.0
+        G[i, :] = apply(fastconv, e)
+        e[s0 - 1] = 0.0
+    return G
+
+
+def _last_left_singular_vector(GS):
+    """U[:, end]' of svd(GS) for a wide matrix: QR of the tall adjoint, then the SVD of the small R'."""
+    R = np.linalg.qr(GS.conj().T, mode="r")
+    U, s, Vh = np.linalg.svd(R.conj().T)
+    return np.conj(U[:, -1])
+
+
+def _assemble(N, row_sets, Indices, Values):
+    rows, cols, vals = [], [], []
+    for rset, ind, val in zip(row_sets, Indices, Values):
+        R, C, V = createIndices(rset, ind, val)
+        rows.append(R)
+        cols.append(C)
+        vals.append(V)
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows) - 1, np.concatenate(cols) - 1)), shape=(N, N)).tocsc()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+# ------------------------------------------------------------------------------------------- 3-D
+# boundary classes in the order upstream pushes / consumes them: interior, 6 faces, 12 edges, 8 corners;
+# per dimension "lo" = first plane (offsets 0,+1), "mid" = interior (-1,0,+1), "hi" = last plane (-1,0)
+_CLASSES_3D = (
+    ("mid", "mid", "mid"),
+    ("lo", "mid", "mid"), ("hi", "mid", "mid"), ("mid", "lo", "mid"), ("mid", "hi", "mid"),
+    ("mid", "mid", "lo"), ("mid", "mid", "hi"),
+    ("lo", "lo", "mid"), ("hi", "lo", "mid"), ("lo", "hi", "mid"), ("hi", "hi", "mid"),
+    ("lo", "mid", "lo"), ("hi", "mid", "lo"), ("lo", "mid", "hi"), ("hi", "mid", "hi"),
+    ("mid", "lo", "lo"), ("mid", "hi", "lo"), ("mid", "lo", "hi"), ("mid", "hi", "hi"),
+    ("lo", "lo", "lo"), ("hi", "lo", "lo"), ("lo", "hi", "lo"), ("hi", "hi", "lo"),
+    ("lo", "lo", "hi"), ("hi", "lo", "hi"), ("lo", "hi", "hi"), ("hi", "hi", "hi"),
+)
+_OFFSETS = {"lo": (0, 1), "mid": (-1, 0, 1), "hi": (-1, 0)}
+
+
+def _rel3(cls, n, m):
+    cx, cy, cz = cls
+    return np.array([dx + n * dy + n * m * dz for dz in _OFFSETS[cz] for dy in _OFFSETS[cy] for dx in _OFFSETS[cx]],
+                    dtype=np.int64)
+
+
+def _centre3(cls, n, m, l):
+    def coord(c, nn):
+        return 1 if c == "lo" else (nn if c == "hi" else int(round(nn / 2)))    # round half to even, like Julia
+    i, j, p = coord(cls[0], n), coord(cls[1], m), coord(cls[2], l)
+    return (p - 1) * n * m + (j - 1) * n + i                                   # changeInd3D
+
+
+def _rows3(n, m, l):
+    Ind = np.arange(1, n * m * l + 1, dtype=np.int64).reshape((n, m, l), order="F")
+    sel = {"lo": slice(0, 1), "mid": slice(1, -1), "hi": slice(-1, None)}
+    return [Ind[sel[cx], sel[cy], sel[cz]].reshape(-1, order="F") for cx, cy, cz in _CLASSES_3D]
+
+
+def sampleG3D(k, X, Y, Z, indS, fastconv, apply=None):
+    """FastConvolution3D.jl:136-160."""
+    return _sample_rows(fastconv, len(X), indS, apply)
+
+
+def _sample_classes_3d(fastconv, n, m, l, apply):
+    """One sampling per class, shared by entriesSparseA3D and entriesSparseG3D: (rel, ind, rows)."""
+    out = []
+    for cls in _CLASSES_3D:
+        rel = _rel3(cls, n, m)
+        ind = _centre3(cls, n, m, l) + rel
+        out.append((rel, ind, _sample_rows(fastconv, n * m * l, ind, apply)))
+    return out
+
+
+def entriesSparseA3D(k, X, Y, Z, fastconv, n, m, l, apply=None, _samples=None):
+    """SparsifyingMatrix3D.jl:1136-1408 -> (Indices, Entries)."""
+    samples = _samples if _samples is not None else _sample_classes_3d(fastconv, n, m, l, apply)
+    N = n * m * l
+    Indices, Entries = [], []
+    for rel, ind, rows in samples:
+        far = np.ones(N, dtype=bool)
+        far[ind - 1] = False
+        Entries.append(_last_left_singular_vector(rows[:, far]))
+        Indices.append(rel)
+    return Indices, Entries
+
+
+def entriesSparseG3D(k, X, Y, Z, fastconv, n, m, l, apply=None, _samples=None):
+    """SparsifyingMatrix3D.jl:963-1135: G restricted to each class's own stencil."""
+    samples = _samples if _samples is not None else _sample_classes_3d(fastconv, n, m, l, apply)
+    return [rows[:, ind - 1] for rel, ind, rows in samples]
+
+
+def buildSparseA3DConv(k, X, Y, Z, fastconv, n, m, l, apply=None, _samples=None):
+    """SparsifyingMatrix3D.jl:1410-1653 (method "normal"): the 27-point matrix As."""
+    Indices, Values = entriesSparseA3D(k, X, Y, Z, fastconv, n, m, l, apply, _samples)
+    return _assemble(n * m * l, _rows3(n, m, l), Indices, Values)
+
+
+def buildSparseAG3DConv(k, X, Y, Z, fastconv, n, m, l, apply=None, _samples=None):
+    """SparsifyingMatrix3D.jl:1659-1917: As*G truncated to the stencils (rows Values[c] * Entries[c])."""
+    samples = _samples if _samples is not None else _sample_classes_3d(fastconv, n, m, l, apply)
+    Indices, Values = entriesSparseA3D(k, X, Y, Z, fastconv, n, m, l, apply, samples)
+    Entries = entriesSparseG3D(k, X, Y, Z, fastconv, n, m, l, apply, samples)
+    ValuesAG = [np.asarray(v).reshape(1, -1) @ e for v, e in zip(Values, Entries)]
+    return _assemble(n * m * l, _rows3(n, m, l), Indices, ValuesAG)
+
+
+def sparsifying_matrices_3d(k, X, Y, Z, fastconv, n, m, l, nu, apply=None):
+    """examples/example3D.jl:56-61 in one sampling pass: (As, Mapproxsp = As + k^2 AG diag(nu))."""
+    samples = _sample_classes_3d(fastconv, n, m, l, apply)
+    As = buildSparseA3DConv(k, X, Y, Z, fastconv, n, m, l, apply, samples)
+    AG = buildSparseAG3DConv(k, X, Y, Z, fastconv, n, m, l, apply, samples)
+    return As, (As + k ** 2 * (AG @ sp.diags(np.asarray(nu, dtype=np.float64)))).tocsc()
+
+
+# ------------------------------------------------------------------------------------------- 2-D
+def _ind_relative_2d(n):
+    # IndRelative of SparsifyingMatrix2D.jl:110-113 (rows: y offset -1,0,+1 ... as written upstream)
+    return np.array([[-n - 1, -n, -n + 1], [-1, 0, 1], [n - 1, n, n + 1]], dtype=np.int64)
+
+
+def _jl(a):
+    """Julia's a[:] (column-major flattening)."""
+    return np.asarray(a).reshape(-1, order="F")
+
+
+def _centres_2d(n, m, strict):
+    """Representative points of the interior and of the four edges (SparsifyingMatrix2D.jl:119,131,140,149,158).
+    Upstream asserts an odd number of points (:106); strict=False takes the nearest interior point on even grids
+    (any interior point gives the same stencil up to the phase ambiguity)."""
+    N = n * m
+    if n % 2 == 1 and m % 2 == 1:
+        return [int(np.rint(v)) for v in (n * (m - 1) / 2 + (n + 1) / 2, n * (m - 1) / 2 + 1, n * (m - 1) / 2,
+                                          (n + 1) / 2, N - (n + 1) / 2)]
+    if strict:
+        raise AssertionError("mod(length(X),2) == 1  (SparsifyingMatrix2D.jl:106)")
+    jm, im = m // 2, n // 2
+    return [im + 1 + n * jm, 1 + n * jm, n * jm, im + 1, N - n + im]
+
+
+def sampleGConv(k, X, Y, indS, fastconv, apply=None):
+    """FastConvolution.jl:278-306."""
+    return _sample_rows(fastconv, len(X), indS, apply)
+
+
+def _classes_2d(n, m, strict):
+    """(stencil for As, stencil order used for G) per class, in upstream's order; the edge orderings of
+    entriesSparseGConv (:293-304) differ from entriesSparseAConv's - kept."""
+    IR = _ind_relative_2d(n)
+    vol, fz1, fz2, fx1, fx2 = _centres_2d(n, m, strict)
+    N = n * m
+    c3, c4 = np.array([0, 1, -n, -n + 1]), np.array([0, -1, -n, -n - 1])
+    return [
+        (vol, _jl(IR), _jl(IR)),
+        (fz1, _jl(IR[:, 1:3]), np.array([0, 1, n, n + 1, -n, -n + 1])),
+        (fz2, _jl(IR[:, 0:2]), np.array([-1, 0, n, n - 1, -n, -n - 1])),
+        (fx1, _jl(IR[1:3, :]), np.array([-1, 0, 1, n, n + 1, n - 1])),
+        (fx2, _jl(IR[0:2, :]), np.array([-1, 0, 1, -n, -n + 1, -n - 1])),
+        (1, _jl(IR[1:3, 1:3]), np.array([0, 1, n, n + 1])),
+        (n, _jl(IR[1:3, 0:2]), np.array([0, -1, n, n - 1])),
+        (N - n + 1, c3, c3),
+        (N, c4, c4),
+    ]
+
+
+def _rows2(n, m):
+    Ind = np.arange(1, n * m + 1, dtype=np.int64).reshape((n, m), order="F")
+    return [_jl(Ind[1:-1, 1:-1]), _jl(Ind[0, 1:-1]), _jl(Ind[-1, 1:-1]), _jl(Ind[1:-1, 0]), _jl(Ind[1:-1, -1]),
+            Ind[0, 0], Ind[-1, 0], Ind[0, -1], Ind[-1, -1]]
+
+
+def entriesSparseAConv(k, X, Y, fastconv, n, m, apply=None, strict=True):
+    """SparsifyingMatrix2D.jl:104-201 -> (Indices, Entries)."""
+    N = n * m
+    Indices, Entries = [], []
+    for centre, relA, relG in _classes_2d(n, m, strict):
+        ind = centre + relA
+        rows = _sample_rows(fastconv, N, ind, apply)
+        far = np.ones(N, dtype=bool)
+        far[ind - 1] = False
+        Entries.append(_last_left_singular_vector(rows[:, far]))
+        Indices.append(np.asarray(relA, dtype=np.int64))
+    return Indices, Entries
+
+
+def entriesSparseGConv(k, X, Y, fastconv, n, m, apply=None, strict=True):
+    """SparsifyingMatrix2D.jl:278-350."""
+    out = []
+    for centre, relA, relG in _classes_2d(n, m, strict):
+        ind = centre + relG
+        out.append(_sample_rows(fastconv, n * m, ind, apply)[:, ind - 1])
+    return out
+
+
+def buildSparseAConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _cache=None):
+    """SparsifyingMatrix2D.jl:888-966."""
+    Indices, Values = _cache if _cache is not None else entriesSparseAConv(k, X, Y, fastconv, n, m, apply, strict)
+    return _assemble(n * m, _rows2(n, m), Indices, Values)
+
+
+def buildSparseAGConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _cache=None):
+    """SparsifyingMatrix2D.jl:441-532: rows Values[c] * Entries[c]."""
+    Indices, Values = _cache if _cache is not None else entriesSparseAConv(k, X, Y, fastconv, n, m, apply, strict)
+    Entries = entriesSparseGConv(k, X, Y, fastconv, n, m, apply, strict)
+    ValuesAG = [np.asarray(v).reshape(1, -1) @ e for v, e in zip(Values, Entries)]
+    return _assemble(n * m, _rows2(n, m), Indices, ValuesAG)

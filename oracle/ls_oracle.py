@@ -371,8 +371,21 @@ def _centres(n, m, strict=True):
     return c
 
 
-def entriesSparseA(k, X, Y, D0, n, m, strict=True):
-    """SparsifyingMatrix2D.jl:5-102: one stencil (row vector) per boundary class."""
+def sampleGConv(k, X, Y, indS, fastconv: FastM):
+    """FastConvolution.jl:278-306: rows of the discrete operator by FFTconvolution of unit vectors (1-based indS)."""
+    indS = np.asarray(indS, dtype=np.int64)
+    G = np.zeros((len(indS), len(X)), dtype=np.complex128)
+    for i, s0 in enumerate(indS):
+        e = np.zeros(len(X), dtype=np.complex128)
+        e[s0 - 1] = 1.0
+        G[i, :] = FFTconvolution(fastconv, e)
+    return G
+
+
+def entriesSparseA(k, X, Y, D0, n, m, strict=True, _sampler=None):
+    """SparsifyingMatrix2D.jl:5-102: one stencil (row vector) per boundary class.
+    (_sampler replaces sampleG: entriesSparseAConv, :104-201, is the same code with sampleGConv.)"""
+    sampleG = _sampler if _sampler is not None else globals()["sampleG"]
     IR = _ind_relative(n)
     N = n * m
     vol, fz1, fz2, fx1, fx2 = _centres(n, m, strict)
@@ -398,11 +411,13 @@ def entriesSparseA(k, X, Y, D0, n, m, strict=True):
     return Indices, Entries
 
 
-def entriesSparseG(k, X, Y, D0, n, m, strict=True):
+def entriesSparseG(k, X, Y, D0, n, m, strict=True, _sampler=None):
     """SparsifyingMatrix2D.jl:205-275: G restricted to each class's stencil.
 
     The edge orderings here differ from entriesSparseA's (a reference quirk, kept).
+    (_sampler: entriesSparseGConv, :278-350, is the same code with sampleGConv.)
     """
+    sampleG = _sampler if _sampler is not None else globals()["sampleG"]
     IR = _ind_relative(n)
     N = n * m
     vol, fz1, fz2, fx1, fx2 = _centres(n, m, strict)
@@ -585,6 +600,25 @@ def buildSparseAG3DConv(k, X, Y, Z, fastconv: FastM3D, n, m, l, _cache=None):
     Entries = entriesSparseG3D(k, X, Y, Z, fastconv, n, m, l)
     ValuesAG = [np.asarray(v).reshape(1, -1) @ e for v, e in zip(Values, Entries)]
     return _assemble_3d(n, m, l, Indices, ValuesAG)
+
+
+def entriesSparseAConv(k, X, Y, fastconv: FastM, n, m, strict=True):
+    """SparsifyingMatrix2D.jl:104-201."""
+    return entriesSparseA(k, X, Y, None, n, m, strict, _sampler=lambda k_, X_, Y_, ind, D0: sampleGConv(k_, X_, Y_, ind, fastconv))
+
+
+def buildSparseAConv(k, X, Y, fastconv: FastM, n, m, strict=True, _cache=None):
+    """SparsifyingMatrix2D.jl:888-966."""
+    Indices, Values = _cache if _cache is not None else entriesSparseAConv(k, X, Y, fastconv, n, m, strict)
+    return _assemble(n, m, Indices, Values)
+
+
+def buildSparseAGConv(k, X, Y, fastconv: FastM, n, m, strict=True, _cache=None):
+    """SparsifyingMatrix2D.jl:441-532 with entriesSparseGConv (:278-350)."""
+    Indices, Values = _cache if _cache is not None else entriesSparseAConv(k, X, Y, fastconv, n, m, strict)
+    Entries = entriesSparseG(k, X, Y, None, n, m, strict, _sampler=lambda k_, X_, Y_, ind, D0: sampleGConv(k_, X_, Y_, ind, fastconv))
+    ValuesAG = [np.asarray(v).reshape(1, -1) @ e for v, e in zip(Values, Entries)]
+    return _assemble(n, m, Indices, ValuesAG)
 
 
 def csc_matvec(A: sp.csc_matrix, x):

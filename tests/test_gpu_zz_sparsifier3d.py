@@ -76,3 +76,29 @@ def test_example3d_preconditioned_gmres_matches_oracle():
     assert hg.isconverged and hg.iters == len(hist_o)
     assert np.max(np.abs(hg["resnorm"] - hist_o) / hist_o) < 1e-8
     assert _rel(ug, uo) < 1e-7
+
+
+def test_sparsifier_built_from_gpu_applies():
+    """As / Msp of examples/example3D.jl:56-61 sampled through FFTconvolution on the GPU operator
+    (343 unit-vector applies), against the oracle's matrices up to the per-row phase (Q5)."""
+    from oracle import ls_oracle as O
+    import scipy.sparse.linalg as spla
+    import fast_solver_lippmann_schwinger_b200 as ls
+    from fast_solver_lippmann_schwinger_b200 import sparsifier as S
+    n, l = 20, 36
+    (x, z), h, k, Mo, As_o, Msp_o, Po = O.example_problem_3d(n, l)
+    X, Y, Z = O.grid3d(x, x, z)
+    Mg = ls.FastM3D(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, Mo.le, n, n, l, k)
+    l0 = Mg.launch_count()
+    As, Msp = S.sparsifying_matrices_3d(k, X, Y, Z, Mg, n, n, l, Mo.nu)
+    assert Mg.launch_count() > l0                                  # the rows came from the device
+    assert As.nnz == As_o.nnz and Msp.nnz == Msp_o.nnz
+    A, B = As.tocsr(), As_o.tocsr()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+    for r in range(0, A.shape[0], 97):                             # per-row unit phase
+        a, b = A.data[A.indptr[r]:A.indptr[r + 1]], B.data[B.indptr[r]:B.indptr[r + 1]]
+        ph = np.vdot(b, a) / abs(np.vdot(b, a))
+        assert np.abs(a - ph * b).max() <= 1e-7 * np.abs(b).max()
+    v = np.random.default_rng(8).standard_normal(n * n * l) + 0j
+    w = spla.splu(Msp).solve(As @ v)
+    assert _rel(w, Po.solve(v)) <= 1e-7
