@@ -99,6 +99,8 @@ function GPUFastM3D(GFFT, nu::Vector{Float64}, ne, me, le, n, m, l, k; L=0.0, Lp
                 out, n, m, l, ne, me, le, nu, g, Float64(k), Float64(L), Float64(Lp), 0))
     return GPUFastM3D(Handle(out[]), nu, ne, me, le, n, m, l, Float64(k), quadRule)
 end
+"GPUFastM3D(M) - GPU twin of a reference `FastM3D`."
+GPUFastM3D(M) = GPUFastM3D(M.GFFT, M.nu, M.ne, M.me, M.le, M.n, M.m, M.l, M.omega; quadRule=M.quadRule)
 size(M::GPUFastM3D, dim) = length(M.nu)       # not defined upstream (Q4) - required by gmres!
 size(M::GPUFastM3D) = (size(M.nu), size(M.nu))
 eltype(M::GPUFastM3D) = ComplexF64
