@@ -12,6 +12,7 @@ import os
 
 import numpy as np
 import pytest
+import scipy.fft as sfft
 import scipy.sparse as sp
 
 from oracle import ls_oracle as O
@@ -227,3 +228,34 @@ def test_sparsifier_3d_restatement():
     u1, h1, c1, _ = gmres(np.zeros(N, complex), lambda v: M * v, rhs, Pl_ldiv=P.solve)
     assert c0 and c1 and len(h1) <= len(h0)
     assert np.linalg.norm(u1 - u0) <= 1e-6 * np.linalg.norm(u0)
+
+
+def test_compact_padding_identity_and_mirror_symmetry():
+    """The device path's central algebra, checked on the CPU: because the input lives on [0, n) and the output is
+    cropped to [0, n), the 4x-padded apply only uses g = ifft2(ifftshift(GFFT)) at the lags (-n, n); wrapping those
+    onto a 2n grid and transforming back gives a 2x-padded apply that is the same operator.  The
+    wrapped kernel is even in every coordinate, so its spectrum is mirror symmetric."""
+    n = 24
+    x, h, k, M = O.pow2_problem_2d(n, ppw=9.3)
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    ref = O.FFTconvolution(M, b)                                   # literal: pad to 4n, full FFTs, crop
+    g4 = sfft.ifft2(sfft.ifftshift(M.GFFT))                        # spatial kernel on the 4n grid
+    lag = np.arange(-n, n)                                         # lags kept, placed at lag mod 2n
+    g2 = np.zeros((2 * n, 2 * n), complex)
+    g2[np.ix_(lag % (2 * n), lag % (2 * n))] = g4[np.ix_(lag % (4 * n), lag % (4 * n))]
+    G2 = sfft.fft2(g2)
+    B = np.zeros((2 * n, 2 * n), complex)
+    B[:n, :n] = b.reshape((n, n), order="F")
+    y = sfft.ifft2(G2 * sfft.fft2(B))[:n, :n].reshape(-1, order="F")
+    assert np.linalg.norm(y - ref) <= 1e-13 * np.linalg.norm(ref)
+    # lag -n is never used by the cropped apply (|i - j| <= n - 1): dropping it makes the kernel exactly even
+    g2e = g2.copy()
+    g2e[n, :] = 0
+    g2e[:, n] = 0
+    y2 = sfft.ifft2(sfft.fft2(g2e) * sfft.fft2(B))[:n, :n].reshape(-1, order="F")
+    assert np.linalg.norm(y2 - ref) <= 1e-13 * np.linalg.norm(ref)
+    G2e = sfft.fft2(g2e)
+    idx = (-np.arange(2 * n)) % (2 * n)
+    scale = np.abs(G2e).max()
+    assert np.abs(G2e - G2e[idx, :]).max() <= 1e-12 * scale and np.abs(G2e - G2e[:, idx]).max() <= 1e-12 * scale
