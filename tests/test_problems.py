@@ -1,0 +1,26 @@
+"""The product-side input builders (bench / examples) against the oracle's restatement of the reference's setup."""
+import numpy as np
+
+from oracle import ls_oracle as O
+
+
+def test_gv_spectrum_2d_quadrant_mirror_is_bit_identical():
+    from fast_solver_lippmann_schwinger_b200.problems import gv_problem_2d, gv_spectrum_2d
+    for n, m in ((16, 16), (12, 20)):
+        h = 1.0 / n
+        k = 2 * np.pi / (9.3 * h)
+        G = gv_spectrum_2d(n, m, h, k)
+        Go = O.gv_spectrum_2d(n, m, h, k)
+        assert G.shape == (4 * n, 4 * m) and np.array_equal(G, Go)
+    nu, G, k, h = gv_problem_2d(32)
+    x, ho, ko, Mo = O.pow2_problem_2d(32)
+    assert h == ho and k == ko and np.array_equal(nu, Mo.nu) and np.array_equal(G, Mo.GFFT)
+
+
+def test_nu_gaussian_3d_grid():
+    from fast_solver_lippmann_schwinger_b200.problems import nu_gaussian_3d_grid
+    n = 12
+    h = 1.0 / n
+    x = -0.5 + h * np.arange(n)
+    X, Y, Z = O.grid3d(x, x, x)
+    assert np.allclose(nu_gaussian_3d_grid(n), O.nu_gaussian_3d(X, Y, Z), rtol=1e-14, atol=1e-18)
