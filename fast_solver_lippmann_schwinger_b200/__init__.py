@@ -6,6 +6,6 @@ Only what the path needs lives here: ``csrc/`` (CUDA kernels + the C ABI of incl
 """
 from ._lib import (DeviceBuffer, LSCudaError, LSUnsupported, PinnedArray, declared_symbols, lib)  # noqa: F401
 from .operators import FastM, FastM3D, FFTconvolution, fastconvolution, mul_  # noqa: F401
-from .krylov import (ConvergenceHistory, GPUSparseMatrixCSC, KrylovWorkspace, SparsifyingPreconditioner,  # noqa: F401
-                     cscmv_, gmres_)
+from .krylov import (ConvergenceHistory, GPUMspFactorization, GPUSparseMatrixCSC, KrylovWorkspace,  # noqa: F401
+                     SparsifyingPreconditioner, cscmv_, gmres_)
 from . import sparsifier  # noqa: F401,E402

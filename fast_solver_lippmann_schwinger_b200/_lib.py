@@ -100,6 +100,12 @@ def lib():
         "ls_mgs_step": (ci, [vp, vp, i64, ci, vp, vp]),
         "ls_gmres": (ci, [vp, vp, vp, SOLVE_CB, vp, vp, vp, ci, i64, dbl, dbl, ci, vp, i64,
                           C.POINTER(i64), C.POINTER(ci), C.POINTER(i64), ci]),
+        "ls_msp_factor": (ci, [C.POINTER(vp), i64, i64, vp, vp, vp]),
+        "ls_msp_solve": (ci, [vp, vp, vp, ci]),
+        "ls_msp_info": (ci, [vp, C.POINTER(i64), C.POINTER(ci), C.POINTER(dbl)]),
+        "ls_gmres_msp": (ci, [vp, vp, vp, vp, vp, vp, ci, i64, dbl, dbl, ci, vp, i64,
+                              C.POINTER(i64), C.POINTER(ci), C.POINTER(i64), ci]),
+        "ls_krylov_last_precond_host_seconds": (ci, [vp, C.POINTER(dbl)]),
         "ls_destroy": (ci, [vp]),
         "ls_sync": (ci, [vp]),
         "ls_timer_start": (ci, [vp]),

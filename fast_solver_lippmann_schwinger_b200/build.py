@@ -75,6 +75,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         link += ["-L" + nccl_dir, "-l:libnccl.so.2", "-Xlinker", "-rpath", "-Xlinker", nccl_dir]
     else:
         link += ["-lnccl"]
+    cublas_dir = _pip_libdir("nvidia.cublas", "libcublas.so.12")      # the copy torch loads too: one cuBLAS per process
+    if cublas_dir:
+        link += ["-L" + cublas_dir, "-l:libcublas.so.12", "-Xlinker", "-rpath", "-Xlinker", cublas_dir]
+    else:
+        link += ["-lcublas"]
     p = subprocess.run(link, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))
@@ -83,17 +88,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def _nccl_libdir():
+def _pip_libdir(module, soname):
     try:
         import importlib.util
-        spec = importlib.util.find_spec("nvidia.nccl")
+        spec = importlib.util.find_spec(module)
         if spec and spec.submodule_search_locations:
             d = os.path.join(list(spec.submodule_search_locations)[0], "lib")
-            if os.path.exists(os.path.join(d, "libnccl.so.2")):
+            if os.path.exists(os.path.join(d, soname)):
                 return d
     except Exception:
         pass
     return None
+
+
+def _nccl_libdir():
+    return _pip_libdir("nvidia.nccl", "libnccl.so.2")
 
 
 if __name__ == "__main__":

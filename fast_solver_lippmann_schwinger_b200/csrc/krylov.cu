@@ -16,6 +16,7 @@
 //   Hessenberg column per GMRES iteration.
 #include "ls_common.cuh"
 #include "spmv.cuh"
+#include <chrono>
 #include <cstring>
 
 using namespace ls;
@@ -293,6 +294,7 @@ struct Krylov : HandleBase {
     cd* d_V = nullptr; long v_cols = 0;
     cd* d_ax = nullptr; cd* d_b = nullptr; cd* d_x = nullptr;
     cd* h_stage = nullptr;        // pinned staging for the preconditioner callback
+    double t_precond_host_s = 0.0; // last ls_gmres: wall time inside D2H + callback + H2D of the Msp solve
 
     int grid_stream(long nn) const { long b = (nn + 255) / 256; return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16); }
 
@@ -503,7 +505,7 @@ int ls_krylov_set_orth(ls_handle h, int orth_meth) {
 int ls_zdotc(ls_handle h, const ls_cdouble* x, const ls_cdouble* y, ls_cdouble* result) {
     KRYLOV_HANDLE(K, h, "ls_zdotc");
     LS_REQUIRE(x && y && result, LS_ERR_INVALID, "ls_zdotc: null pointer");
-    K->dot((const cd*)x, (const cd*)y, K->d_scal, K->stream);
+    { int rc = K->dot((const cd*)x, (const cd*)y, K->d_scal, K->stream); if (rc) return rc; }
     LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, K->stream));
     LS_CUDA_TRY(cudaStreamSynchronize(K->stream));
     result->re = K->h_scal[0];
@@ -514,7 +516,7 @@ int ls_zdotc(ls_handle h, const ls_cdouble* x, const ls_cdouble* y, ls_cdouble* 
 int ls_dznrm2(ls_handle h, const ls_cdouble* x, double* result) {
     KRYLOV_HANDLE(K, h, "ls_dznrm2");
     LS_REQUIRE(x && result, LS_ERR_INVALID, "ls_dznrm2: null pointer");
-    K->nrm2((const cd*)x, K->d_scal, K->stream);
+    { int rc = K->nrm2((const cd*)x, K->d_scal, K->stream); if (rc) return rc; }
     LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, sizeof(double), cudaMemcpyDeviceToHost, K->stream));
     LS_CUDA_TRY(cudaStreamSynchronize(K->stream));
     *result = K->h_scal[0];
@@ -551,27 +553,35 @@ int ls_mgs_step(ls_handle h, const ls_cdouble* V, int64_t ldv, int k, ls_cdouble
     return LS_OK;
 }
 
-int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve, void* user,
-             const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol, double abstol,
-             int initially_zero, double* resnorm_hist, int64_t hist_cap, int64_t* niter, int* converged,
-             int64_t* mv_products, int memloc) {
-    KRYLOV_HANDLE(K, kh, "ls_gmres");
-    LS_REQUIRE(op_h && b && x, LS_ERR_INVALID, "ls_gmres: null argument");
-    HandleBase* op = reinterpret_cast<HandleBase*>(op_h);
+// Common driver behind ls_gmres (host callback for Msp^-1) and ls_gmres_msp (device-resident Msp^-1).
+static int gmres_driver(Krylov* K, HandleBase* op, SpM* As, MspBase* msp, ls_solve_cb msp_solve, void* user,
+                        const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol, double abstol,
+                        int initially_zero, double* resnorm_hist, int64_t hist_cap, int64_t* niter, int* converged,
+                        int64_t* mv_products, int memloc) {
     LS_REQUIRE(op->op_size() == K->n, LS_ERR_INVALID, "ls_gmres: operator size %ld != workspace size %ld",
                (long)op->op_size(), (long)K->n);
-    SpM* As = reinterpret_cast<SpM*>(as_h);
-    if (As) LS_REQUIRE(As->kind == KIND_SPM && As->nrows == K->n && As->ncols == K->n, LS_ERR_INVALID,
-                       "ls_gmres: As must be an N x N sparse-matrix handle");
+    if (As) LS_REQUIRE(As->kind == KIND_SPM && As->nrows == K->n && As->x_len() == K->n, LS_ERR_INVALID,
+                       "ls_gmres: As must be an N x N sparse-matrix handle (or the row slab of one, ls_spm_create_dist)");
+    if (msp) LS_REQUIRE(msp->kind == KIND_MSP && msp->n == K->n, LS_ERR_INVALID,
+                        "ls_gmres_msp: the Msp factorisation has %ld unknowns, the operator %ld", (long)msp->n, (long)K->n);
     const long n = K->n;
     if (restart <= 0) restart = 20;
     LS_REQUIRE(restart <= 64, LS_ERR_UNSUPPORTED, "ls_gmres: restart > 64 is not supported");
-    if (maxiter <= 0) maxiter = n;     // callers with sharded vectors pass the global N
+    if (maxiter < 0) maxiter = n;      // default; callers with sharded vectors pass the global N.  0 = no iteration.
     // all work is enqueued on the operator's stream so that its apply orders with our kernels
     cudaStream_t s = op->stream;
-    K->comm = op->nccl_comm();      // sharded operator: dots / norms are all-reduced on its communicator
-    LS_REQUIRE(!(K->comm && (As || msp_solve)), LS_ERR_UNSUPPORTED,
-               "ls_gmres: the preconditioner is not sharded (SURVEY.md section 8(e)); use Pl = Identity with a sharded operator");
+    // sharded operator: dots / norms are all-reduced on its communicator for the duration of this solve only
+    struct CommScope { Krylov* K; ~CommScope() { K->comm = nullptr; } } comm_scope{K};
+    K->comm = op->nccl_comm();
+    if (K->comm) {
+        // Sharded vectors.  As must be the row slab living on the same communicator (its halo exchange is a
+        // collective); the Msp solve is not sharded: only a host callback (which may gather / scatter) is accepted.
+        LS_REQUIRE(!As || (As->halo > 0 && As->comm == K->comm), LS_ERR_INVALID,
+                   "ls_gmres: with a sharded operator As must come from ls_spm_create_dist on the same operator");
+        LS_REQUIRE(!msp, LS_ERR_UNSUPPORTED, "ls_gmres_msp: the device Msp factorisation is single-GPU");
+    } else if (As) {
+        LS_REQUIRE(As->halo == 0, LS_ERR_INVALID, "ls_gmres: a row-slab As needs the sharded operator it was created on");
+    }
     const size_t vb = (size_t)n * sizeof(cd);
     if (K->v_cols < restart + 1) {
         if (K->d_V) K->dfree(K->d_V);
@@ -602,10 +612,12 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
     cd* V = K->d_V;
     const long ldv = n;
     const int gs = K->grid_stream(n);
+    K->t_precond_host_s = 0.0;
 
-    // ldiv!(Pl, v):  v <- Msp^-1 (As v)   (preconditioner.jl:147-166); As on the GPU, Msp^-1 through the callback
+    // ldiv!(Pl, v):  v <- Msp^-1 (As v)   (preconditioner.jl:147-166).  As on the GPU; Msp^-1 either on the GPU
+    // (msp: the factorisation of ls_msp_factor, no PCIe traffic) or through the host callback.
     auto precond = [&](cd* v) -> int {
-        if (!As && !msp_solve) return LS_OK;
+        if (!As && !msp_solve && !msp) return LS_OK;
         cd* cur = v;
         if (As) {
             int rc = As->mv_dev(make_double2(1.0, 0.0), v, make_double2(0.0, 0.0), K->d_ax, s);
@@ -613,12 +625,19 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
             K->launches++;
             cur = K->d_ax;
         }
-        if (msp_solve) {
+        if (msp) {
+            int rc = msp->solve_dev(cur, v, s);
+            if (rc) return rc;
+            K->launches += msp->launches_per_solve;
+        } else if (msp_solve) {
+            const auto t0 = std::chrono::steady_clock::now();
             LS_CUDA_TRY(cudaMemcpyAsync(K->h_stage, cur, vb, cudaMemcpyDeviceToHost, s));
             LS_CUDA_TRY(cudaStreamSynchronize(s));
             int crc = msp_solve(user, reinterpret_cast<ls_cdouble*>(K->h_stage), n);
             LS_REQUIRE(crc == 0, LS_ERR_CALLBACK, "ls_gmres: the Msp solve callback returned %d", crc);
             LS_CUDA_TRY(cudaMemcpyAsync(v, K->h_stage, vb, cudaMemcpyHostToDevice, s));
+            LS_CUDA_TRY(cudaStreamSynchronize(s));
+            K->t_precond_host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         } else {
             LS_CUDA_TRY(cudaMemcpyAsync(v, cur, vb, cudaMemcpyDeviceToDevice, s));
         }
@@ -657,9 +676,10 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
     const double tol = fmax(reltol * current, abstol);
     int k = 1;
     int64_t iteration = 0, nh = 0;
-    auto done = [&](int64_t it) { return it >= maxiter || current <= tol; };
+    // IterativeSolvers gmres.jl: converged(g) = residual <= tol; done(g, it) = it >= maxiter || converged(g)
+    auto is_converged = [&]() { return current <= tol; };
     std::vector<cplx> y;
-    while (!done(iteration)) {
+    while (!(iteration >= maxiter || is_converged())) {
         // expand!: V_{k+1} = Pl^-1 (A V_k)
         cd* w = V + (long)k * ldv;
         rc = op->apply_dev(V + (long)(k - 1) * ldv, w, LS_APPLY_FASTCONVOLUTION);
@@ -681,7 +701,9 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
         accumulator += nullvec[k].re * nullvec[k].re + nullvec[k].im * nullvec[k].im;
         current = rbeta / sqrt(accumulator);
         k++;
-        if (k == restart + 1 || done(iteration + 1)) {
+        // gmres.jl iterate(): x is formed at a restart or at convergence only - when maxiter lands inside a cycle the
+        // caller gets the x of the last restart, exactly as upstream - and the cycle restarts whenever not converged.
+        if (k == restart + 1 || is_converged()) {
             std::vector<cplx> Hc(H);
             solve_least_squares(Hc, ldh, beta, k - 1, y);
             LS_CUDA_TRY(cudaMemcpyAsync(K->d_y, y.data(), (size_t)(k - 1) * sizeof(cd), cudaMemcpyHostToDevice, s));
@@ -689,7 +711,7 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
             K->launches++;
             LS_CUDA_TRY(cudaStreamSynchronize(s));   // y (host vector) must outlive the H2D copy
             k = 1;
-            if (!done(iteration + 1)) {
+            if (!is_converged()) {
                 rc = init(false, beta);
                 if (rc) return rc;
                 accumulator = 1.0;
@@ -706,6 +728,35 @@ int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve
     if (niter) *niter = iteration;
     if (converged) *converged = current <= tol ? 1 : 0;
     if (mv_products) *mv_products = mv;
+    return LS_OK;
+}
+
+int ls_gmres(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_solve_cb msp_solve, void* user,
+             const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol, double abstol,
+             int initially_zero, double* resnorm_hist, int64_t hist_cap, int64_t* niter, int* converged,
+             int64_t* mv_products, int memloc) {
+    KRYLOV_HANDLE(K, kh, "ls_gmres");
+    LS_REQUIRE(op_h && b && x, LS_ERR_INVALID, "ls_gmres: null argument");
+    return gmres_driver(K, reinterpret_cast<HandleBase*>(op_h), reinterpret_cast<SpM*>(as_h), nullptr, msp_solve, user, b, x,
+                        restart, maxiter, reltol, abstol, initially_zero, resnorm_hist, hist_cap, niter, converged,
+                        mv_products, memloc);
+}
+
+int ls_gmres_msp(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_handle msp_h,
+                 const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol, double abstol,
+                 int initially_zero, double* resnorm_hist, int64_t hist_cap, int64_t* niter, int* converged,
+                 int64_t* mv_products, int memloc) {
+    KRYLOV_HANDLE(K, kh, "ls_gmres_msp");
+    LS_REQUIRE(op_h && msp_h && b && x, LS_ERR_INVALID, "ls_gmres_msp: null argument");
+    return gmres_driver(K, reinterpret_cast<HandleBase*>(op_h), reinterpret_cast<SpM*>(as_h), reinterpret_cast<MspBase*>(msp_h),
+                        nullptr, nullptr, b, x, restart, maxiter, reltol, abstol, initially_zero, resnorm_hist, hist_cap,
+                        niter, converged, mv_products, memloc);
+}
+
+int ls_krylov_last_precond_host_seconds(ls_handle kh, double* seconds) {
+    KRYLOV_HANDLE(K, kh, "ls_krylov_last_precond_host_seconds");
+    LS_REQUIRE(seconds, LS_ERR_INVALID, "ls_krylov_last_precond_host_seconds: null pointer");
+    *seconds = K->t_precond_host_s;
     return LS_OK;
 }
 

@@ -296,6 +296,79 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     for (int a = AR; a < E; ++a) o[(long)(a * T) * la.out_es] = accs[(a - AR) * TH];
 }
 
+// ---- middle, fused, 2x padding, no accumulator registers ("swap" variant, mode A) ----------------------------
+// Same arithmetic and the same bits as k_mid_fused with nr = 2 and direct spectrum loads.  k_mid_fused keeps the
+// input line in shared memory AND 16 accumulators in registers (248 registers: two 128-thread CTAs per SM, and the
+// pass is latency-bound at 8 warps per SM).  With two sub-transforms only one thread-private buffer is needed: it
+// holds the input line x while r = 0 is transformed, then x and the r = 0 result trade places (each thread swaps
+// its own 16 elements, no barrier), and the r = 2 result is combined with the held one on the way out.  Without
+// the accumulators the kernel fits 168 registers and 66 KB of shared memory: three CTAs per SM.
+// GL: how the spectrum chunk reaches the multiply.  0: all E values requested before the last butterfly stage and
+// held in registers across it (64 more live registers); 1: the chunk is pulled into L2 by prefetches issued before
+// the last butterfly stage and loaded right at the multiply (the other CTAs of the SM cover the L2 latency).
+template <int N, int MINB, int GL>
+__global__ void __launch_bounds__(GeoA<N>::THREADS, MINB)
+k_mid_swap(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restrict__ TAB, const LineAddr la, long line0) {
+    typedef Map<N, false> M;
+    constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC, TH = GeoA<N>::THREADS;
+    extern __shared__ __align__(128) cd sm[];
+    M mp;
+    cd* ex = sm;
+    cd* hold = sm + LPC * N + threadIdx.x;          // element a of this thread at hold[a*TH]
+    cd* tw1 = sm + 2 * LPC * N;
+    load_tw1<N>(tw1, TAB);
+    const long L = line0 + (long)blockIdx.x * LPC + mp.line;
+    const int t = mp.t;
+    const TwState<N> tw = make_tw<N>(t, TAB, tw1);
+    const cd* gline = G + L * 2L * N;               // chunk rr of line L at gline + rr*N
+    cd v[E];
+    {
+        const cd* p = in + line_in(la, L) + (long)t * la.in_es;
+#pragma unroll
+        for (int a = 0; a < E; ++a) v[a] = p[(long)(a * T) * la.in_es];
+#pragma unroll
+        for (int a = 0; a < E; ++a) hold[a * TH] = v[a];
+    }
+    __syncthreads();   // tw1 visible
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = 2 * rr;
+        const cd* g = gline + (long)rr * N;
+        if constexpr (GL == 0) {
+            cd gv[E];
+            fft_fwd<N>(v, t, r, ex, mp.lay, tw, [&]() {
+#pragma unroll
+                for (int e = 0; e < E; ++e) gv[e] = __ldg(&g[t + T * e]);
+            });
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], gv[e]);
+        } else {
+            fft_fwd<N>(v, t, r, ex, mp.lay, tw, [&]() {
+                if ((t & 7) == 0) {       // one request per 128-byte line
+#pragma unroll
+                    for (int e = 0; e < E; ++e) prefetch_l2(&g[t + T * e]);
+                }
+            });
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], __ldg(&g[t + T * e]));
+        }
+        fft_inv<N>(v, t, r, ex, mp.lay, tw);
+        if (rr == 0) {
+            // x and the r = 0 result trade places
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                const cd xa = hold[a * TH];
+                hold[a * TH] = v[a];
+                v[a] = xa;
+            }
+        }
+    }
+    cd* o = out + line_out(la, L) + (long)t * la.out_es;
+    o[0] = cadd(hold[0], v[0]);
+#pragma unroll
+    for (int a = 1; a < E; ++a) o[(long)(a * T) * la.out_es] = cfmac(v[a], c64(2 * a * (16 / E)), hold[a * TH]);
+}
+
 // cp.async helpers (inverse pass staging; experiment kernels)
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -390,17 +463,26 @@ k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __res
 // ---- host-side launchers ----------------------------------------------------------------
 namespace lsk {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute and a process may hold handles on several
+// GPUs (ls_set_device): opt in once per (kernel instantiation, device).  `done` = the call site's static bit mask.
+template <class K> inline cudaError_t smem_optin(K kernel, int smem, unsigned long long& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) done |= bit;
+    return e;
+}
+
 template <int N, bool B>
 inline cudaError_t launch_fwd(cudaStream_t s, long nlines, const cd* in, const double* nu, cd* out, const cd* TAB,
                               const LineAddr& la) {
     constexpr int smem = Smem<N, B>::fwd_bytes;
     constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_fwd_pruned<N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    { cudaError_t e = smem_optin(k_fwd_pruned<N, B>, smem, optin); if (e != cudaSuccess) return e; }
     k_fwd_pruned<N, B><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, nu, out, TAB, la, 0);
     return cudaPeekAtLastError();
 }
@@ -410,13 +492,19 @@ inline cudaError_t launch_mid(cudaStream_t s, long nlines, const cd* in, cd* out
                               const LineAddr& la) {
     constexpr int smem = GSM ? Smem<N, B>::mid_bytes : Smem<N, B>::mid_bytes_direct;
     constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_mid_fused<N, B, GSM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    { cudaError_t e = smem_optin(k_mid_fused<N, B, GSM, 1>, smem, optin); if (e != cudaSuccess) return e; }
     k_mid_fused<N, B, GSM, 1><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, out, G, TAB, la, 0);
+    return cudaPeekAtLastError();
+}
+
+template <int N, int MINB, int GL>
+inline cudaError_t launch_mid_swap(cudaStream_t s, long nlines, const cd* in, cd* out, const cd* G, const cd* TAB,
+                                   const LineAddr& la) {
+    constexpr int smem = (2 * GeoA<N>::LPC * N + EngTab<N>::TW1N) * (int)sizeof(cd);
+    static unsigned long long optin = 0;
+    { cudaError_t e = smem_optin(k_mid_swap<N, MINB, GL>, smem, optin); if (e != cudaSuccess) return e; }
+    k_mid_swap<N, MINB, GL><<<(unsigned)(nlines / GeoA<N>::LPC), GeoA<N>::THREADS, smem, s>>>(in, out, G, TAB, la, 0);
     return cudaPeekAtLastError();
 }
 
@@ -425,12 +513,8 @@ inline cudaError_t launch_inv(cudaStream_t s, long nlines, const cd* in, const c
                               double scale, const LineAddr& la) {
     constexpr int smem = Smem<N, B>::fwd_bytes + (PF == 2 ? Smem<N, B>::LPC * N * (int)sizeof(cd) : 0);
     constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_inv_pruned<N, B, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    { cudaError_t e = smem_optin(k_inv_pruned<N, B, PF>, smem, optin); if (e != cudaSuccess) return e; }
     k_inv_pruned<N, B, PF><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, bsrc, out, TAB, scale, la, 0);
     return cudaPeekAtLastError();
 }

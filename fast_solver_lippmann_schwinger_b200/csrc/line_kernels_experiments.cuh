@@ -75,12 +75,8 @@ template <int N, int MINB>
 inline cudaError_t launch_mid_lean(cudaStream_t s, long nlines, const cd* in, cd* out, const cd* G, const cd* TAB,
                                    const LineAddr& la) {
     constexpr int smem = (2 * GeoB<N>::LPC * N + EngTab<N>::TW1N) * (int)sizeof(cd) + 16;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_mid_lean<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    { cudaError_t e = smem_optin(k_mid_lean<N, MINB>, smem, optin); if (e != cudaSuccess) return e; }
     k_mid_lean<N, MINB><<<(unsigned)(nlines / GeoB<N>::LPC), GeoB<N>::THREADS, smem, s>>>(in, out, G, TAB, la, 0);
     return cudaPeekAtLastError();
 }
@@ -156,12 +152,8 @@ template <int N>
 inline cudaError_t launch_mid_persist(cudaStream_t s, long nlines, const cd* in, cd* out, const cd* G, const cd* TAB,
                                       const LineAddr& la, int ctas) {
     constexpr int smem = (3 * GeoA<N>::LPC * N + EngTab<N>::TW1N) * (int)sizeof(cd);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_mid_persist<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    { cudaError_t e = smem_optin(k_mid_persist<N>, smem, optin); if (e != cudaSuccess) return e; }
     const long ngroups = nlines / GeoA<N>::LPC;
     const long grid = ngroups < ctas ? ngroups : ctas;
     k_mid_persist<N><<<(unsigned)grid, GeoA<N>::THREADS, smem, s>>>(in, out, G, TAB, la, ngroups);
@@ -253,12 +245,8 @@ inline cudaError_t launch_mid_cluster(cudaStream_t s, long nlines, const cd* in,
                                       const LineAddr& la) {
     constexpr int smem = Smem<N, B>::fwd_bytes;
     constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_mid_cluster<N, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    { cudaError_t e = smem_optin(k_mid_cluster<N, B, MINB>, smem, optin); if (e != cudaSuccess) return e; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(4 * (nlines / LPC)));
     cfg.blockDim = dim3(TH);

@@ -17,7 +17,9 @@
 #include "ls_common.cuh"
 #include "op2d_base.cuh"
 #include "line_kernels.cuh"
-#include "line_kernels_experiments.cuh"
+#ifdef LS_EXPERIMENTS
+#include "line_kernels_experiments.cuh"   // measured-and-rejected variants: only with -DLS_EXPERIMENTS (profiles/r1_b_notes.md)
+#endif
 
 using namespace ls;
 using namespace lsk;
@@ -62,11 +64,8 @@ __global__ void k_permute_g2d(const cd* __restrict__ gin, cd* __restrict__ gout,
 
 template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
     constexpr int smem = Smem<N, false>::fwd_bytes;
-    static bool attr = false;
-    if (!attr) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(k_fwd_pruned<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    LS_CUDA_TRY(smem_optin(k_fwd_pruned<N, false>, smem, optin));
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
     LineAddr la{1L << 40, op->n, 0, 1, op->pn, 0, 1};
     la.nr = op->nr;
@@ -81,11 +80,8 @@ template <int N, bool GSM, int MINB, int ASM = 0> int launch_mid_v(Op2D* op) {
     if (extra < 0) { const char* e = getenv("LS_P2_EXTRA_SMEM"); extra = e ? atoi(e) : 0; }
     const int smem = (GSM ? Smem<N, false>::mid_bytes : Smem<N, false>::mid_bytes_direct) + extra
                      + ASM * GeoA<N>::THREADS * (int)sizeof(cd);
-    static bool attr = false;
-    if (!attr) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused<N, false, GSM, MINB, ASM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    LS_CUDA_TRY(smem_optin(k_mid_fused<N, false, GSM, MINB, ASM>, smem, optin));
     dim3 grid((unsigned)(op->pn / GeoA<N>::LPC));
     // line = x slot sx; point j at A[sx + pn*j]; output: cw adjacent x-slots interleaved, C[(sx/cw)*(cw*m) + cw*j + sx%cw]
     const long cw = op->cw;
@@ -98,13 +94,11 @@ template <int N, bool GSM, int MINB, int ASM = 0> int launch_mid_v(Op2D* op) {
     op->launches++;
     return LS_OK;
 }
+#ifdef LS_EXPERIMENTS
 template <int N, int ASM> int launch_mid_dual(Op2D* op) {
     const int smem = (3 * GeoA<N>::LPC * N + EngTab<N>::TW1N + ASM * GeoA<N>::THREADS) * (int)sizeof(cd);
-    static bool attr = false;
-    if (!attr) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(k_mid_fused_dual<N, ASM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    LS_CUDA_TRY(smem_optin(k_mid_fused_dual<N, ASM>, smem, optin));
     dim3 grid((unsigned)(op->ne / GeoA<N>::LPC));
     op->phase_begin(1);
     k_mid_fused_dual<N, ASM><<<grid, GeoA<N>::THREADS, smem, op->stream>>>(
@@ -113,7 +107,34 @@ template <int N, int ASM> int launch_mid_dual(Op2D* op) {
     op->launches++;
     return LS_OK;
 }
+#endif
+// 2x padding: the swap kernel (no accumulator registers, three CTAs per SM; see line_kernels.cuh)
+template <int N> int launch_mid_swap_op(Op2D* op) {
+    const long cw = op->cw;
+    LineAddr la{cw, 1, cw, op->pn, 1, cw * op->m, cw};
+    la.nr = 2;
+    static int gl = -1, minb = -1;   // LS_P2_GLOAD: 0 spectrum held in registers across the last stage, 1 L2 prefetch + load at the multiply
+    if (gl < 0) { const char* e = getenv("LS_P2_GLOAD"); gl = e ? atoi(e) : 0; }
+    if (minb < 0) { const char* e = getenv("LS_P2_MINB"); minb = e ? atoi(e) : 3; }
+    constexpr int MB = (GeoA<N>::THREADS <= 128 ? 3 : 1);
+    op->phase_begin(1);
+    cudaError_t e;
+    if (minb == 2 && MB == 3) e = gl ? lsk::launch_mid_swap<N, 2, 1>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la)
+                                     : lsk::launch_mid_swap<N, 2, 0>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la);
+    else e = gl ? lsk::launch_mid_swap<N, MB, 1>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la)
+                : lsk::launch_mid_swap<N, MB, 0>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la);
+    op->phase_end();
+    op->launches++;
+    LS_CUDA_TRY(e);
+    return LS_OK;
+}
 template <int N> int launch_mid(Op2D* op) {
+    static int kernel = -1;          // LS_P2_KERNEL: 1 (default) swap kernel, 0 k_mid_fused (accumulators in registers)
+    if (kernel < 0) { const char* e = getenv("LS_P2_KERNEL"); kernel = e ? atoi(e) : 1; }
+    if (op->nr == 2 && kernel == 1) return launch_mid_swap_op<N>(op);
+#ifndef LS_EXPERIMENTS
+    return launch_mid_v<N, false, 1>(op);       // spectrum straight from HBM into registers, requested before the last butterfly stage
+#else
     static int variant = -1;
     if (op->nr != 4) return launch_mid_v<N, false, 1>(op);      // the experiment kernels below are 4x-padding only
     // variants measured on B200 at 2048^2 (profiles/r1_b_notes.md): 1 = spectrum straight from HBM into
@@ -151,14 +172,12 @@ template <int N> int launch_mid(Op2D* op) {
     if (variant == 2) return launch_mid_v<N, false, 3, 4>(op);
     if (variant == 3) return launch_mid_v<N, false, 3, 2>(op);
     return launch_mid_v<N, false, 1>(op);
+#endif
 }
 template <int N, int PF> int launch_inv_v(Op2D* op, const cd* bsrc, cd* y, double scale) {
     constexpr int smem = Smem<N, false>::fwd_bytes + (PF == 2 ? Smem<N, false>::LPC * N * (int)sizeof(cd) : 0);
-    static bool attr = false;
-    if (!attr) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(k_inv_pruned<N, false, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static unsigned long long optin = 0;
+    LS_CUDA_TRY(smem_optin(k_inv_pruned<N, false, PF>, smem, optin));
     dim3 grid((unsigned)(op->m / GeoA<N>::LPC));
     // line = column j; slot sx at C[(sx/cw)*(cw*m) + cw*j + sx%cw]: adjacent lanes read adjacent slots
     const long cw = op->cw;

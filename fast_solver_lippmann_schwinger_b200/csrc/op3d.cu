@@ -19,7 +19,9 @@
 // All-to-all volume per rank and direction: 16*nr*N*(P-1)/P^2 bytes.
 #include "ls_common.cuh"
 #include "line_kernels.cuh"
-#include "line_kernels_experiments.cuh"
+#ifdef LS_EXPERIMENTS
+#include "line_kernels_experiments.cuh"   // measured-and-rejected variants: only with -DLS_EXPERIMENTS
+#endif
 #include "dist.cuh"
 #include "gv_spectrum.cuh"
 
@@ -192,8 +194,12 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
 #define C3T(N) launch_mid<N, true, true>(s, nelc * me, op->d_A2, op->d_A2, Gc, op->d_TABl, la)
 #define C3L2(N) launch_mid_lean<N, 2>(s, nelc * me, op->d_A2, op->d_A2, Gc, op->d_TABl, la)
 #define C3L3(N) launch_mid_lean<N, (GeoB<N>::THREADS <= 128 ? 3 : 1)>(s, nelc * me, op->d_A2, op->d_A2, Gc, op->d_TABl, la)
+#ifdef LS_EXPERIMENTS
             if (variant == 1 || nr != 4) { LS3_DISPATCH(l, C3T); } else if (variant == 2) { LS3_DISPATCH(l, C3L2); }
             else if (variant == 3) { LS3_DISPATCH(l, C3L3); } else { LS3_DISPATCH(l, C3); }
+#else
+            if (variant != 0) { LS3_DISPATCH(l, C3T); } else { LS3_DISPATCH(l, C3); }
+#endif
             op->phase_end(); op->launches++;
             LS_CUDA_TRY(e);
         }

@@ -33,4 +33,14 @@ struct SpM : HandleBase {
     int mv_dev(cd alpha, const cd* x, cd beta, cd* y, cudaStream_t s);
 };
 
+// Device-resident factorisation of the sparsified system matrix Msp (msp.cu): what `MspInv \\ .` of
+// preconditioner.jl:138,159 becomes when the whole preconditioned GMRES loop stays on the GPU.
+constexpr uint32_t KIND_MSP = 0x4c534d53;
+struct MspBase : HandleBase {
+    long n = 0;
+    int launches_per_solve = 0;
+    // out <- Msp^-1 rhs on device pointers (out may alias rhs), enqueued on stream s
+    virtual int solve_dev(const cd* rhs, cd* out, cudaStream_t s) = 0;
+};
+
 }  // namespace ls

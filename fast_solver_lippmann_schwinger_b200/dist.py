@@ -172,3 +172,48 @@ class GPUSparseMatrixCSCSharded(_Handle):
         return self.mv(x)
 
     __matmul__ = __mul__
+
+
+class ShardedSparsifyingPreconditioner:
+    """``SparsifyingPreconditioner(Msp, As)`` (preconditioner.jl:27-58) next to a FastM3DSharded operator.
+    ``As`` is sharded by rows on the GPUs (its halo exchange runs inside every GMRES iteration); the sparse direct
+    solve with Msp is not sharded: rank 0 holds ``lu(Msp)`` on the host, and the ls_solve_cb
+    callback gathers the slabs to it, solves, and scatters the result (CPU tensors on a gloo group)."""
+
+    def __init__(self, Msp, As, op, group=None):
+        import torch
+        import torch.distributed as dist
+        import scipy.sparse.linalg as spla
+        from ._lib import SOLVE_CB
+        self.As = GPUSparseMatrixCSCSharded(As, op)
+        self.MspGPU = None
+        self.rank, self.nranks = op.rank, op.nranks
+        if group is None and self.nranks > 1:
+            group = dist.new_group(backend="gloo") if dist.get_backend() != "gloo" else dist.group.WORLD
+        self.group = group
+        self.MspInv = spla.splu(Msp.tocsc()) if self.rank == 0 else None
+        ranges = [vector_range(op.n, op.m, op.l, r, self.nranks) for r in range(self.nranks)]
+
+        def _cb(user, vptr, n):
+            try:
+                buf = (C.c_double * (2 * n)).from_address(vptr)
+                v = np.frombuffer(buf, dtype=np.complex128)
+                if self.nranks == 1:
+                    v[:] = self.MspInv.solve(v)
+                    return 0
+                mine = torch.from_numpy(v.view(np.float64))
+                parts = [torch.empty(2 * (b - a), dtype=torch.float64) for a, b in ranges] if self.rank == 0 else None
+                dist.gather(mine, parts, dst=0, group=self.group)
+                outs = None
+                if self.rank == 0:
+                    full = np.concatenate([p.numpy().view(np.complex128) for p in parts])
+                    sol = self.MspInv.solve(full)
+                    outs = [torch.from_numpy(np.ascontiguousarray(sol[a:b]).view(np.float64)) for a, b in ranges]
+                dist.scatter(mine, outs, src=0, group=self.group)
+                return 0
+            except Exception:      # never let an exception cross the C ABI
+                return 1
+        self._cb = SOLVE_CB(_cb)
+
+    def destroy(self):
+        self.As.destroy()

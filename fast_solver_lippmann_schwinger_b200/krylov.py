@@ -11,9 +11,12 @@
     gmres!(x, A, b; Pl, log, restart, maxiter, reltol, ...)    gmres_(x, A, b, Pl=, log=, ...)
       IterativeSolvers.jl (un-vendored), examples/example.jl:85
 
-Scope note: only the `As*b` half of ldiv! is on the GPU hot path.  The sparse
-direct solve `MspInv \\ .` (UMFPACK / MKL PARDISO upstream) stays on the host with the caller;
-here scipy's SuperLU plays UMFPACK's part and is reached through the ls_solve_cb callback.
+    lu(Msp)  (MspInv, preconditioner.jl:35)                    GPUMspFactorization(Msp, n, m)  [solverType="GPU"]
+
+The sparse direct solve `MspInv \\ .` (UMFPACK / MKL PARDISO upstream) has two routes here:
+solverType="GPU" factorises Msp on the device (ls_msp_factor: nested dissection, 2-D 9-point matrices) so the
+whole preconditioned GMRES loop runs without PCIe traffic; solverType="UMFPACK" keeps it on the host with the
+caller - scipy's SuperLU plays UMFPACK's part and is reached through the ls_solve_cb callback.
 """
 from __future__ import annotations
 
@@ -92,22 +95,58 @@ def cscmv_(transa, alpha, matdescra, A: GPUSparseMatrixCSC, x, beta, y):
     return A.mv(x, y, alpha=alpha, beta=beta)
 
 
+class GPUMspFactorization(_Handle):
+    """``lu(Msp)`` (preconditioner.jl:35) on the GPU: nested-dissection factorisation of the 9-point matrix Msp of
+    the n x m grid (ls_msp_factor).  ``solve(b)`` = ``MspInv \\ b`` on host arrays or DeviceBuffers."""
+
+    def __init__(self, Msp, n, m):
+        super().__init__()
+        nrows, ncols, colptr, rowval, nzval = _julia_csc(Msp)
+        self.n, self.m = int(n), int(m)
+        if nrows != ncols or nrows != self.n * self.m:
+            raise ValueError("DimensionMismatch: Msp is %d x %d, the grid has %d unknowns" % (nrows, ncols, self.n * self.m))
+        self.N = nrows
+        check(lib().ls_msp_factor(C.byref(self._h), self.n, self.m, ptr(colptr), ptr(rowval), ptr(nzval)))
+        fb, dep, sec = C.c_int64(), C.c_int(), C.c_double()
+        check(lib().ls_msp_info(self.handle, C.byref(fb), C.byref(dep), C.byref(sec)))
+        self.factor_bytes, self.depth, self.factor_seconds = int(fb.value), int(dep.value), float(sec.value)
+
+    def solve(self, b, out=None):
+        if isinstance(b, DeviceBuffer):
+            out = b if out is None else out
+            check(lib().ls_msp_solve(self.handle, ptr(b), ptr(out), _lib.MEM_DEVICE))
+            return out
+        b = _as_c128(b, self.N, "b")
+        out = np.empty(self.N, dtype=np.complex128) if out is None else out
+        check(lib().ls_msp_solve(self.handle, ptr(b), ptr(out), _lib.MEM_HOST))
+        return out
+
+
 class SparsifyingPreconditioner:
     """``struct SparsifyingPreconditioner`` (preconditioner.jl:27-58).
 
-    As lives on the GPU; MspInv is the host sparse LU (SuperLU here, UMFPACK upstream).
+    As lives on the GPU.  MspInv is the host sparse LU (solverType "UMFPACK" / "MKLPARDISO" as upstream; SuperLU
+    here) or, with solverType="GPU" and the grid size, the device factorisation (no host work inside gmres!).
     """
 
-    def __init__(self, Msp, As, solverType="UMFPACK"):
+    def __init__(self, Msp, As, solverType="UMFPACK", grid=None):
         import scipy.sparse.linalg as spla
-        if solverType not in ("UMFPACK", "MKLPARDISO"):
+        if solverType not in ("UMFPACK", "MKLPARDISO", "GPU"):
             raise ValueError("unknown solverType %r" % (solverType,))
         self.solverType = solverType
         self.Msp = Msp.tocsc()
         self.As_host = As
         self.As = GPUSparseMatrixCSC(As)
-        self.MspInv = spla.splu(self.Msp)          # lu(Msp), preconditioner.jl:35
         self.N = self.Msp.shape[0]
+        self.MspGPU = None
+        if solverType == "GPU":
+            if grid is None:
+                raise ValueError("solverType='GPU' needs grid=(n, m)")
+            self.MspGPU = GPUMspFactorization(self.Msp, grid[0], grid[1])
+            self.MspInv = self.MspGPU
+            self._cb = C.cast(None, SOLVE_CB)
+            return
+        self.MspInv = spla.splu(self.Msp)          # lu(Msp), preconditioner.jl:35
 
         def _cb(user, vptr, n):
             try:
@@ -122,6 +161,11 @@ class SparsifyingPreconditioner:
     def solve(self, b):
         """``M \\ b``  preconditioner.jl:132-145."""
         return self.MspInv.solve(self.As * b)
+
+    def destroy(self):
+        self.As.destroy()
+        if self.MspGPU is not None:
+            self.MspGPU.destroy()
 
     def ldiv_(self, b):
         """``ldiv!(M, b)``  preconditioner.jl:147-166 (in place)."""
@@ -192,7 +236,7 @@ def gmres_(x, A, b, Pl=None, abstol=0.0, reltol=None, restart=None, maxiter=None
     N = A.size(1)
     reltol = float(np.sqrt(np.finfo(np.float64).eps)) if reltol is None else float(reltol)
     restart = min(20, N) if restart is None else int(restart)
-    maxiter = getattr(A, "N_global", N) if maxiter is None else int(maxiter)
+    maxiter = getattr(A, "N_global", N) if maxiter is None else max(int(maxiter), 0)
     ws = workspace if workspace is not None else KrylovWorkspace(N)
     if orth_meth not in ORTH_METHODS:
         raise ValueError("orth_meth must be one of %s" % sorted(ORTH_METHODS))
@@ -205,14 +249,23 @@ def gmres_(x, A, b, Pl=None, abstol=0.0, reltol=None, restart=None, maxiter=None
         if not (isinstance(x, np.ndarray) and x.dtype == np.complex128 and x.shape == (N,) and x.flags.c_contiguous):
             raise ValueError("DimensionMismatch: x must be a contiguous complex128 vector of length %d" % N)
     cap = maxiter if maxiter < 1_000_000 else 1_000_000
-    hist = np.zeros(cap, dtype=np.float64)
+    hist = np.zeros(max(cap, 1), dtype=np.float64)
     niter, conv, mv = C.c_int64(), C.c_int(), C.c_int64()
-    as_h = Pl.As.handle if Pl is not None else None
-    cb = Pl._cb if Pl is not None else C.cast(None, SOLVE_CB)
-    check(lib().ls_gmres(ws.handle, A.handle, as_h, cb, None, ptr(b), ptr(x), restart, maxiter, reltol, float(abstol),
-                         1 if initially_zero else 0, ptr(hist), cap, C.byref(niter), C.byref(conv), C.byref(mv),
-                         _lib.MEM_DEVICE if dev else _lib.MEM_HOST))
+    as_h = Pl.As.handle if (Pl is not None and Pl.As is not None) else None
+    memloc = _lib.MEM_DEVICE if dev else _lib.MEM_HOST
+    if Pl is not None and getattr(Pl, "MspGPU", None) is not None:
+        check(lib().ls_gmres_msp(ws.handle, A.handle, as_h, Pl.MspGPU.handle, ptr(b), ptr(x), restart, maxiter, reltol,
+                                 float(abstol), 1 if initially_zero else 0, ptr(hist), cap, C.byref(niter), C.byref(conv),
+                                 C.byref(mv), memloc))
+    else:
+        cb = Pl._cb if Pl is not None else C.cast(None, SOLVE_CB)
+        check(lib().ls_gmres(ws.handle, A.handle, as_h, cb, None, ptr(b), ptr(x), restart, maxiter, reltol, float(abstol),
+                             1 if initially_zero else 0, ptr(hist), cap, C.byref(niter), C.byref(conv), C.byref(mv), memloc))
     if not log:
         return x
     n = min(int(niter.value), cap)
-    return x, ConvergenceHistory(hist[:n].copy(), int(niter.value), bool(conv.value), int(mv.value), restart)
+    h = ConvergenceHistory(hist[:n].copy(), int(niter.value), bool(conv.value), int(mv.value), restart)
+    sec = C.c_double()
+    check(lib().ls_krylov_last_precond_host_seconds(ws.handle, C.byref(sec)))
+    h.msp_host_seconds = float(sec.value)      # D2H + host Msp solve + H2D inside the loop (0 with solverType="GPU")
+    return x, h

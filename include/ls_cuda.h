@@ -158,13 +158,37 @@ typedef int (*ls_solve_cb)(void* user, ls_cdouble* v_inout, int64_t n);
 /* gmres!(x, A, b; Pl, abstol, reltol, restart, maxiter, log=true, initially_zero) with the Krylov
  * basis resident on the GPU.  A = operator handle; left preconditioner ldiv!(Pl, v) =
  * msp_solve(As*v) (preconditioner.jl:147-166): `As` nullable, `msp_solve` nullable.
- * restart <= 0 -> min(20, N); maxiter <= 0 -> N (inner iterations); reltol as given
- * (upstream default sqrt(eps)).  resnorm_hist receives the logged residual per inner
- * iteration (history[:resnorm], example.jl:86).  b, x: host or device per memloc.           */
+ * restart <= 0 -> min(20, N); maxiter < 0 -> N (inner iterations), maxiter == 0 -> no iteration;
+ * reltol as given (upstream default sqrt(eps)).  resnorm_hist receives the logged residual per
+ * inner iteration (history[:resnorm], example.jl:86).  b, x: host or device per memloc.
+ * As upstream, x is formed at a restart or at convergence only: when maxiter lands inside a cycle
+ * the x of the last restart is returned.  With a sharded operator (ls_op3d_create_dist) the vectors
+ * are this rank's slabs, dots and norms are all-reduced on the operator's communicator, `As` must
+ * come from ls_spm_create_dist on the same operator and `msp_solve` receives the rank's slab
+ * (gathering it is the callback's business; the Msp solve itself is not sharded).            */
 int ls_gmres(ls_handle krylov, ls_handle op, ls_handle As, ls_solve_cb msp_solve, void* user,
              const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol,
              double abstol, int initially_zero, double* resnorm_hist, int64_t hist_cap,
              int64_t* niter, int* converged, int64_t* mv_products, int memloc);
+
+/* ---- device-resident Msp^-1: `MspInv = lu(Msp)` preconditioner.jl:35 (UMFPACK; :41-55 PARDISO) and the solve
+ * `MspInv \ (As*b)` of every GMRES iteration (:138,142,159,163).  Msp = As + k^2 AG diag(nu) (examples/example.jl:67)
+ * is a 9-point stencil matrix on the n x m grid (unknown i + n*j, x fastest), given as Julia holds it (1-based CSC).
+ * Factorised on the GPU by geometric nested dissection (multifrontal, partial pivoting inside the pivot blocks);
+ * every solve is a fixed sequence of batched matrix-vector kernels - no PCIe traffic, no host work per iteration.
+ * 2-D only (a 27-point 3-D matrix keeps the ls_solve_cb route): entries outside the 9-point pattern -> LS_ERR_UNSUPPORTED. */
+int ls_msp_factor(ls_handle* out, int64_t n, int64_t m, const int64_t* colptr, const int64_t* rowval,
+                  const ls_cdouble* nzval);
+/* x <- Msp^-1 rhs (x may alias rhs); host or device pointers per memloc */
+int ls_msp_solve(ls_handle msp, const ls_cdouble* rhs, ls_cdouble* x, int memloc);
+int ls_msp_info(ls_handle msp, int64_t* factor_bytes, int* depth, double* factor_seconds);
+/* ls_gmres with ldiv!(Pl, v) = Msp^-1 (As v) entirely on the device (`msp` from ls_msp_factor, `As` nullable) */
+int ls_gmres_msp(ls_handle krylov, ls_handle op, ls_handle As, ls_handle msp,
+                 const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol,
+                 double abstol, int initially_zero, double* resnorm_hist, int64_t hist_cap,
+                 int64_t* niter, int* converged, int64_t* mv_products, int memloc);
+/* wall time the last ls_gmres spent in D2H + msp_solve callback + H2D (the "Msp-solve" column of SURVEY.md H1) */
+int ls_krylov_last_precond_host_seconds(ls_handle krylov, double* seconds);
 
 /* ---- handle services ------------------------------------------------------------------ */
 int ls_destroy(ls_handle h);

@@ -124,10 +124,11 @@ def gmres(x, A_mul, b, Pl_ldiv=None, abstol=0.0, reltol=None, restart=None, maxi
     history = []
     iteration = 0
 
-    def done(it):
-        return it >= maxiter or current <= tol
+    def converged():
+        return current <= tol
 
-    while not done(iteration):
+    # gmres.jl: done(g, it) = it >= maxiter || converged(g)
+    while not (iteration >= maxiter or converged()):
         # expand!
         w = pl(A_mul(V[:, k - 1]))
         mv += 1
@@ -141,11 +142,13 @@ def gmres(x, A_mul, b, Pl_ldiv=None, abstol=0.0, reltol=None, restart=None, maxi
         accumulator += abs(nullvec[k]) ** 2
         current = rbeta / np.sqrt(accumulator)
         k += 1
-        if k == restart + 1 or done(iteration + 1):
+        # gmres.jl iterate(): x is formed at a restart or at convergence only (if maxiter lands inside a cycle the
+        # caller gets the x of the last restart), and the cycle restarts whenever the solve has not converged
+        if k == restart + 1 or converged():
             y = solve_least_squares(H, beta, k)
             x += V[:, :k - 1] @ y
             k = 1
-            if not done(iteration + 1):
+            if not converged():
                 beta = init(False)
                 accumulator = 1.0
                 rbeta = beta
