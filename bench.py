@@ -9,20 +9,29 @@ wavelength, Gaussian-bump contrast, complex128, one apply per step.  2-D grids r
 ("replicas only"), so for N > 1 every rank applies its own replica and
 `value` is the sum (weak scaling, no data-path collective).
 
-`value`  : applies/s with b and y resident in HBM (CUDA events on the handle's stream).
-`e2e`    : the same apply through the public host API (`FastM * b` on host arrays) with the
-           host->device copy of b from pinned memory and the device->host copy of y inside
-           the timed region.
-`roofline`: the dominant kernel (P2, k_mid_fused) - algorithmic bytes 384*N per launch over
-           its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+`value`   : applies/s with b and y resident in HBM (CUDA events on the handle's stream).
+`e2e`     : the same apply through the public host API (`FastM * b` on host arrays) with the
+            host->device copy of b from pinned memory and the device->host copy of y inside
+            the timed region.
+`roofline`: the dominant kernel (P2, the fused middle pass).  `achieved` = the bytes the pass
+            as implemented has to move (2x compact padding: 128 N per launch - input slab 32 N,
+            spectrum 64 N, output 32 N) over its CUDA-event duration,
+            against MEASURED_PEAKS.json hbm_gbs.  The SURVEY.md 8(d) figure (literal pruned-4x pass
+            structure, 384 N) is reported beside it as `survey_model_*`, never as the fraction.
 `cpu_baseline`: the oracle's literal restatement of fastconvolution (scipy.fft, all host
-           cores) on the same workload, a bounded sample of applies.
-`--impl reference` times that CPU path alone (the reference is Julia; Julia/FFTW are not in
-           this image, so the oracle port is the reference arm - see DESIGN.md).
+            cores) on the same workload, a bounded sample of applies.
+Extra objects in the same line: `parity` (64^3 sharded apply / SpMV / GMRES against the oracle, at
+every N, outside the timed region), `apply3d` (256^3) and `apply3d_512` (sharded for N > 1, with the
+single-GPU time measured in the same run and the strong-scaling efficiency), `gmres` (Pl = Identity),
+`gmres_precond` (config 3: plasma contrast, sparsifying preconditioner with As and Msp^-1 on the GPU),
+`krylov_kernels`, `device_peaks` (FP64 and copy microbenchmarks run live).
+`--impl reference` times the CPU path alone (the reference is Julia; Julia/FFTW are not in
+            this image, so the oracle port is the reference arm - see DESIGN.md).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -46,6 +55,15 @@ def measured_peaks():
             d = json.load(fh)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_counters():
+    """Per-launch counters of the dominant kernels from the committed ncu captures (profiles/r2_counters.json)."""
+    p = os.path.join(ROOT, "profiles", "r2_counters.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return {}
 
 
 class ClockSampler:
@@ -157,39 +175,133 @@ def workload_config(n):
             "parallelism": "replica per GPU (2-D path does not shard)"}
 
 
-def bench_3d(args, ls, lsd, rank, world, local_rank, dist, peak, peak_src):
-    """3-D 256^3 apply, slab-decomposed over `world` GPUs (strong scaling; world == 1: one GPU)."""
+def device_peaks(lib):
+    dfma, dadd, cp = C.c_double(), C.c_double(), C.c_double()
+    rc = lib.ls_test_device_peaks(C.byref(dfma), C.byref(dadd), C.byref(cp))
+    if rc != 0:
+        return None
+    return {"fp64_fma_tflops": dfma.value, "fp64_add_tera_lane_instr_per_s": dadd.value, "copy_kernel_GBs": cp.value,
+            "how": "ls_test_device_peaks: 8 independent DFMA (DADD) chains per thread, 8 CTAs of 256 threads per SM, best of 3; "
+                   "plain 1 GiB double2 copy kernel, read + write bytes, best of 5"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def parity_block(ls, lsd, rank, world, dist):
+    """64^3 sharded apply, sharded sparsifier SpMV and a 12-iteration sharded GMRES against the CPU oracle, outside
+    any timed region.  Rank 0 evaluates the oracle and broadcasts the references (FastConvolution3D.jl:31-63,
+    preconditioner.jl:159, IterativeSolvers gmres!)."""
+    import scipy.sparse as sp
+    n = 64
+    N = n ** 3
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    iters = 12
+    rng = np.random.default_rng(1234)
+    b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    xg = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    # 27-point matrix with the structure of the 3-D sparsifier (one coefficient vector per boundary class)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util_sparse import stencil27
+    A = stencil27(n, n, n, seed=21, classes=True)
+    ref = [None]
+    t0 = time.perf_counter()
+    if rank == 0:
+        from oracle import ls_oracle as O
+        from oracle.gmres_is import gmres as gmres_oracle
+        x = -0.5 + h * np.arange(n)
+        Mo = O.buildFastConvolution3D(x, x, x, h, k, O.nu_gaussian_3d)
+        y_ref = Mo * b
+        X = O.grid3d(x, x, x)[0]
+        u_inc = np.exp(1j * k * X)
+        rhs = -(Mo * u_inc - u_inc)                       # examples/example3D.jl:71-72
+        _, hist_o, _, _ = gmres_oracle(np.zeros(N, complex), lambda v: Mo * v, rhs, maxiter=iters)
+        ref[0] = (Mo.nu, y_ref, rhs, hist_o, A @ xg)
+    if dist is not None:
+        dist.broadcast_object_list(ref, src=0)
+    nu, y_ref, rhs, hist_o, ys_ref = ref[0]
+    oracle_s = time.perf_counter() - t0
+    a, b_ = lsd.vector_range(n, n, n, rank, world)
+    uid = lsd.broadcast_unique_id(rank) if world > 1 else None
+    M = lsd.FastM3DSharded(nu[a:b_], n, n, n, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid)
+    y = M * np.ascontiguousarray(b[a:b_])
+    e_apply = float(np.linalg.norm(y - y_ref[a:b_]) / np.linalg.norm(y_ref[a:b_]))
+    if world > 1:
+        As = lsd.GPUSparseMatrixCSCSharded(A, M)
+    else:
+        As = ls.GPUSparseMatrixCSC(A)
+    ys = As * np.ascontiguousarray(xg[a:b_])
+    e_spmv = float(np.linalg.norm(ys - ys_ref[a:b_]) / np.linalg.norm(ys_ref[a:b_]))
+    xs, hg = ls.gmres_(np.zeros(b_ - a, complex), M, np.ascontiguousarray(rhs[a:b_]), maxiter=iters, log=True)
+    e_hist = float(np.max(np.abs(hg["resnorm"] - hist_o) / hist_o)) if hg.iters == len(hist_o) else float("inf")
+    errs = [e_apply, e_spmv, e_hist]
+    if dist is not None:
+        import torch
+        t = torch.tensor(errs, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        errs = [float(v) for v in t]
+    fmt = As.format
+    As.destroy()
+    M.destroy()
+    return {"grid": [n, n, n], "ranks": world, "apply_rel_l2": errs[0], "spmv_rel_l2": errs[1], "gmres_hist_rel": errs[2],
+            "gmres_iters": int(hg.iters), "spmv_format": fmt,
+            "tolerances": {"apply_rel_l2": 1e-12, "spmv_rel_l2": 1e-13, "gmres_hist_rel": 1e-8},
+            "passed": bool(errs[0] <= 1e-12 and errs[1] <= 1e-13 and errs[2] <= 1e-8),
+            "how": "max over ranks of the slab errors against the CPU oracle (rank 0 evaluates it, %.0f s, outside the timed regions); "
+                   "SpMV = the %s row-slab kernel with the NCCL halo exchange for N > 1" % (oracle_s, fmt)}
+
+
+def bench_3d(args, n, ls, lsd, rank, world, dist, peak, peak_src, counters, want_single=True):
+    """3-D n^3 apply, slab-decomposed over `world` GPUs (strong scaling; world == 1: one GPU).  For world > 1 rank 0
+    also times the single-GPU operator in the same run so that the strong-scaling efficiency is measured, not quoted."""
     from fast_solver_lippmann_schwinger_b200.problems import nu_gaussian_3d_grid
-    n = args.n3
     h = 1.0 / n
     k = 2 * np.pi / (10 * h)
     N = n ** 3
+
+    def barrier(Mx=None):
+        if Mx is not None:
+            Mx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    nu_full = nu_gaussian_3d_grid(n)
+    steps = max(5, min(args.steps, 20))
+    single_ms = None
+    if world > 1 and want_single:
+        if rank == 0:
+            M1 = lsd.FastM3DSharded(nu_full, n, n, n, k, 1.8 * n * h, 4.0 * n * h, 0, 1, None)
+            rng1 = np.random.default_rng(4321)
+            d1 = ls.DeviceBuffer.from_host(rng1.standard_normal(N) + 1j * rng1.standard_normal(N))
+            d2 = ls.DeviceBuffer(16 * N)
+            for _ in range(3):
+                M1.mul_(d2, d1)
+            M1.sync()
+            M1.timer_start()
+            for _ in range(steps):
+                M1.mul_(d2, d1)
+            single_ms = M1.timer_stop() / steps
+            M1.destroy()
+            d1.free(); d2.free()
+        barrier()
     uid = lsd.broadcast_unique_id(rank) if world > 1 else None
     a, b_ = lsd.vector_range(n, n, n, rank, world)
-    nu = nu_gaussian_3d_grid(n)[a:b_]
-    M = lsd.FastM3DSharded(nu, n, n, n, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid)
+    M = lsd.FastM3DSharded(nu_full[a:b_], n, n, n, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid)
+    del nu_full
     rng = np.random.default_rng(4321 + rank)
     b = rng.standard_normal(b_ - a) + 1j * rng.standard_normal(b_ - a)
     db = ls.DeviceBuffer.from_host(b)
     dy = ls.DeviceBuffer(b.nbytes)
-
-    def barrier():
-        M.sync()
-        if dist is not None:
-            dist.barrier()
-
-    steps = max(5, min(args.steps, 20))
     for _ in range(3):
         M.mul_(dy, db)
-    barrier()
+    barrier(M)
     M.profile_enable(True)
     l0 = M.launch_count()
-    barrier()
+    barrier(M)
     M.timer_start()
     for _ in range(steps):
         M.mul_(dy, db)
     ms = M.timer_stop()
-    barrier()
+    barrier(M)
     ph, cnt = M.profile_read(7)
     M.profile_enable(False)
     launches = M.launch_count() - l0
@@ -197,60 +309,131 @@ def bench_3d(args, ls, lsd, rank, world, local_rank, dist, peak, peak_src):
     hb = ls.PinnedArray((b_ - a,)); hy = ls.PinnedArray((b_ - a,))
     hb.array[:] = b
     M._apply(hb.array, hy.array, 0)
-    barrier()
+    barrier(M)
     t0 = time.perf_counter()
     for _ in range(3):
         M._apply(hb.array, hy.array, 0)
     e2e_s = time.perf_counter() - t0
     if dist is not None:
         import torch
-        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, single_ms if single_ms is not None else 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
+        single_ms = float(t[2]) if float(t[2]) > 0 else None
     per = [p / steps for p in ph]                   # per apply (a phase runs once per x-slot chunk)
     ms_step = ms / steps
     p3 = per[2]
-    compact = True                          # compact 2x padding on one GPU and on the sharded operator
-    # P3 bytes per rank.  implemented: spectrum + padded slab read + write of the pass as run;
-    # survey: SURVEY.md 8(d) accounting of the literal pruned-4x pass structure (1024N + 256N + 256N)
-    impl_p3 = (256.0 if compact else 1536.0) * N / world
-    impl_apply = (568.0 if compact else 2360.0) * N / world
-    alg_p3 = 1536.0 * N / world
+    # bytes the passes as implemented (2x compact padding) have to move, per rank: P3 = spectrum 128N + slab read and
+    # write 2 x 64N; whole apply 568N.  SURVEY.md 8(d) accounts the literal pruned-4x structure.
+    impl_p3 = 256.0 * N / world
+    impl_apply = 568.0 * N / world
+    key = "p3_%d" % n
     out = {
         "metric": "ls_operator_applies_per_s_3d", "value": steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "scaling": "strong" if world > 1 else "single", "ms_per_apply": ms_step, "grid": [n, n, n], "padded": [4 * n] * 3,
         "workload": "3-D Greengard_Vico LS apply %d^3 (reference padding %d^3), spectrum generated on device, z-slab sharded over %d GPU(s)" % (n, 4 * n, world),
-        "padding_used": "2x (kernel restricted to the lags the cropped apply touches; same operator to 1e-16)" if compact else "4x (literal)",
+        "padding_used": "2x (kernel restricted to the lags the cropped apply touches; same operator to 1e-16)",
         "gpu_launches": launches,
         "phase_ms": {"P1_x_fwd": per[0], "P2_y_fwd": per[1], "P3_z_fused": per[2], "P4_y_inv": per[3], "P5_x_inv": per[4],
                      "a2a_fwd": per[5], "a2a_back": per[6]},
-        "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P3: fused z-line FFT, spectrum multiply, inverse)", "achieved": alg_p3 / (p3 * 1e-3) / 1e9,
-                     "peak": peak, "unit": "GB/s", "frac": alg_p3 / (p3 * 1e-3) / 1e9 / peak,
-                     "algorithmic_bytes_model": "SURVEY.md 8(d), literal pruned-4x pass structure: 1536N per apply for this pass",
-                     "implemented_bytes_per_launch": impl_p3, "implemented_achieved": impl_p3 / (p3 * 1e-3) / 1e9,
-                     "implemented_frac": impl_p3 / (p3 * 1e-3) / 1e9 / peak,
-                     "traffic": ((3.2213e9 + 1.0451e9) if compact else (21.4755e9 + 4.2829e9) / world) if n == 256 else None,
-                     "traffic_source": "ncu --set full at 256^3: r1_g compact dram read 3.22 GB + write 1.05 GB; r1_e literal 21.48 + 4.28 GB (profiles/)",
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_p3, "launch_ms": p3},
-        "apply_roofline": {"survey_bytes_per_apply_per_gpu": 2360.0 * N / world,
-                           "survey_frac": 2360.0 * N / world / (ms_step * 1e-3) / 1e9 / peak,
-                           "implemented_bytes_per_apply_per_gpu": impl_apply,
-                           "implemented_frac": impl_apply / (ms_step * 1e-3) / 1e9 / peak},
+        "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P3: fused z-line FFT, spectrum multiply, inverse)",
+                     "achieved": impl_p3 / (p3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": impl_p3 / (p3 * 1e-3) / 1e9 / peak,
+                     "bytes_per_launch": impl_p3, "bytes_model": "implemented pass, 2x compact padding: 256 N / ranks",
+                     "traffic": counters.get(key, {}).get("dram_bytes"), "traffic_source": counters.get(key, {}).get("source"),
+                     "peak_source": peak_src, "launch_ms": p3,
+                     "survey_model_bytes_per_launch": 1536.0 * N / world,
+                     "survey_model_note": "SURVEY.md 8(d) counts the literal pruned-4x pass (1536 N); the implemented pass needs 1/6 of it, so that figure is not a roofline fraction"},
+        "apply_roofline": {"bytes_per_apply_per_gpu": impl_apply, "achieved": impl_apply / (ms_step * 1e-3) / 1e9,
+                           "frac": impl_apply / (ms_step * 1e-3) / 1e9 / peak,
+                           "survey_model_bytes_per_apply_per_gpu": 2360.0 * N / world},
         "e2e": {"value": 3 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * (b_ - a), "d2h_bytes_per_step": 16 * (b_ - a)},
     }
     if world > 1:
         xb = lsd.exchange_bytes_per_rank(n, n, n, world, pad=2)
         a2a = 0.5 * (per[5] + per[6])
         compute = sum(per[0:5])
-        out["nvlink"] = {"bytes_sent_per_gpu_per_transpose": xb, "a2a_ms": a2a, "achieved_GBs": xb / (a2a * 1e-3) / 1e9,
-                         "peak_GBs": 770.0, "frac": xb / (a2a * 1e-3) / 1e9 / 770.0,
+        out["nvlink"] = {"bytes_sent_per_gpu_per_transpose": xb, "a2a_ms": a2a, "achieved_GBs": xb / (a2a * 1e-3) / 1e9 if a2a > 0 else None,
+                         "peak_GBs": 770.0, "frac": xb / (a2a * 1e-3) / 1e9 / 770.0 if a2a > 0 else None,
                          "x_slot_chunks": cnt[1] // max(steps, 1),
-                         "overlap": "transposes run chunk by chunk on a second (high-priority) stream while P2-P4 work on the neighbouring "
-                                    "chunks; a2a_ms is the sum of the chunk transfers measured on that stream (they share SMs and HBM with the line kernels)",
                          "compute_ms": compute, "exposed_exchange_ms": ms_step - compute,
                          "peak_source": "measured peer copy per direction (B200_PROFILING.md)"}
+        if single_ms:
+            out["single_gpu_ms_per_apply"] = single_ms
+            out["strong_scaling_speedup"] = single_ms / ms_step
+            out["strong_scaling_efficiency"] = single_ms / ms_step / world
     M.destroy()
+    db.free(); dy.free()
+    return out
+
+
+def bench_gmres3d(args, n, ls, lsd, rank, world, dist):
+    """Config 5: n^3 layered scatterer, GMRES(20) to reltol 1e-8 with Pl = Identity on the slab-decomposed operator
+    (examples/example3D.jl:71-79: rhs = -(A u_inc - u_inc), u_inc = exp(i k x)); every dot / norm is an all-reduced scalar."""
+    from fast_solver_lippmann_schwinger_b200.problems import nu_layered_3d_slab
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    p0, p1 = lsd.slab_range(n, rank, world)
+    a, b_ = lsd.vector_range(n, n, n, rank, world)
+    uid = lsd.broadcast_unique_id(rank) if world > 1 else None
+    M = lsd.FastM3DSharded(nu_layered_3d_slab(n, p0, p1), n, n, n, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid)
+    x = -0.5 + h * np.arange(n)
+    u_inc = np.ascontiguousarray(np.broadcast_to(np.exp(1j * k * x)[:, None, None], (n, n, p1 - p0)).reshape(-1, order="F"))
+    du = ls.DeviceBuffer.from_host(u_inc)
+    dr = ls.DeviceBuffer(16 * (b_ - a))
+    M.mul_(dr, du)
+    M.sync()
+    rhs = -(dr.to_host() - u_inc)
+    del u_inc
+    db = ls.DeviceBuffer.from_host(rhs)
+    dx = ls.DeviceBuffer.from_host(np.zeros(b_ - a, complex))
+    ws = ls.KrylovWorkspace(b_ - a)
+    ls.gmres_(dx, M, db, reltol=1e-8, maxiter=3, workspace=ws)          # warm-up: basis allocation, first launches
+    dx = ls.DeviceBuffer.from_host(np.zeros(b_ - a, complex))
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    _, hist = ls.gmres_(dx, M, db, reltol=1e-8, maxiter=args.gmres3d_maxiter, log=True, workspace=ws)
+    dt = time.perf_counter() - t0
+    # true residual of the returned iterate (one more sharded apply, norm by all-reduce through torch)
+    M.mul_(dr, dx)
+    M.sync()
+    res = dr.to_host() - rhs
+    num, den = float(np.vdot(res, res).real), float(np.vdot(rhs, rhs).real)
+    ar_us = None
+    if dist is not None:
+        import torch
+        t = torch.tensor([num, den, dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t[:2], op=dist.ReduceOp.SUM)
+        tt = t[2:].clone()
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        num, den, dt = float(t[0]), float(t[1]), float(tt[0])
+        probe = torch.zeros(2, device="cuda", dtype=torch.float64)
+        for _ in range(20):
+            dist.all_reduce(probe)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(200):
+            dist.all_reduce(probe)
+        torch.cuda.synchronize()
+        ar_us = (time.perf_counter() - t1) / 200 * 1e6
+    its = max(hist.iters, 1)
+    # scalar all-reduces of a solve: per inner iteration k one per Gram-Schmidt column plus the norm, plus one per (re)start
+    n_ar = sum(min(i % 20, 19) + 2 for i in range(hist.iters)) + hist.mvps - hist.iters + 1
+    out = {"metric": "gmres_time_to_1e-8 (3-D, config 5)", "grid": [n, n, n], "n_gpus": world,
+           "contrast": "4 horizontal layers (0.05, 0.10, 0.02, 0.08) inside the box |x|,|y|,|z| < 0.48, piecewise constant in z",
+           "k": k, "preconditioner": "Identity", "restart": 20, "time_s": dt, "iters": hist.iters, "converged": hist.isconverged,
+           "mv_products": hist.mvps, "ms_per_iter": 1e3 * dt / its,
+           "final_rel_residual_estimate": float(hist["resnorm"][-1] / hist["resnorm"][0]) if hist.iters else None,
+           "true_rel_residual": float(np.sqrt(num / den)) if den > 0 else None,
+           "scalar_allreduces": int(n_ar) if world > 1 else 0}
+    if ar_us is not None:
+        out["allreduce_latency_us"] = ar_us
+        out["allreduce_share_estimate"] = n_ar * ar_us * 1e-6 / dt
+        out["allreduce_share_note"] = "count of scalar all-reduces x the latency of a 2-double NCCL all-reduce measured back to back on the same GPUs"
+    M.destroy()
+    for buf in (du, dr, db, dx):
+        buf.free()
     return out
 
 
@@ -276,12 +459,95 @@ def bench_gmres(args, ls, M, n, k, h, peak):
     _, hist2 = ls.gmres_(dx2, M, db, reltol=1e-8, maxiter=args.gmres_maxiter, log=True, workspace=ws, orth_meth="DGKS")
     dt2 = time.perf_counter() - t0
     dgks = {"time_s": dt2, "iters": hist2.iters, "converged": hist2.isconverged, "ms_per_iter": 1e3 * dt2 / max(hist2.iters, 1)}
+    # end to end: host rhs in, host u out (pinned), everything else resident
+    hr = ls.PinnedArray((N,)); hx = ls.PinnedArray((N,))
+    hr.array[:] = rhs
+    hx.array[:] = 0
+    t0 = time.perf_counter()
+    _, hist3 = ls.gmres_(hx.array, M, hr.array, reltol=1e-8, maxiter=args.gmres_maxiter, log=True, workspace=ws)
+    dt3 = time.perf_counter() - t0
     alg_iter = (248.0 + 64.0 * 10.5 + 48.0 + 32.0) * N         # apply (2x padding) + fused MGS (avg k = 10.5) + normalise
     return {"metric": "gmres_time_to_1e-8", "time_s": dt, "iters": hist.iters, "converged": hist.isconverged, "restart": 20,
             "mv_products": hist.mvps, "ms_per_iter": 1e3 * dt / it, "final_rel_residual": float(hist["resnorm"][-1] / hist["resnorm"][0]) if hist.iters else None,
-            "preconditioner": "Identity (the Msp direct solve is host-side and out of scope, SURVEY.md H1)",
-            "algorithmic_bytes_per_iter": alg_iter, "hbm_frac": alg_iter / (dt / it) / 1e9 / peak,
-            "orth_meth": "ModifiedGramSchmidt (upstream default)", "with_orth_meth_DGKS": dgks}
+            "preconditioner": "Identity",
+            "bytes_per_iter": alg_iter, "hbm_frac": alg_iter / (dt / it) / 1e9 / peak,
+            "orth_meth": "ModifiedGramSchmidt (upstream default)", "with_orth_meth_DGKS": dgks,
+            "e2e_host_rhs_in_u_out": {"time_s": dt3, "iters": hist3.iters, "h2d_bytes": 32 * N, "d2h_bytes": 16 * N}}
+
+
+def bench_gmres_precond(args, ls, peak):
+    """Config 3 (tests/plasma_example.jl:20-68,160-176 at BASELINE's grid): discontinuous plasma contrast, Greengard_Vico
+    operator, sparsifying preconditioner built from GPU operator applies (buildSparseAConv / buildSparseAGConv),
+    As*b and Msp^-1 on the GPU, GMRES(20) to reltol 1e-8.  Columns as SURVEY.md H1 asks: GPU loop, Msp solve, PCIe."""
+    import scipy.sparse as sp
+    from fast_solver_lippmann_schwinger_b200 import sparsifier as S
+    from fast_solver_lippmann_schwinger_b200.problems import nu_plasma_2d
+    n = args.precond_n
+    N = n * n
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    x = -0.5 + h * np.arange(n)
+    X = np.repeat(x[:, None], n, axis=1).reshape(-1, order="F")
+    Y = np.repeat(x[None, :], n, axis=0).reshape(-1, order="F")
+    nu = np.asarray(nu_plasma_2d(X, Y), dtype=np.float64)
+    t0 = time.perf_counter()
+    M = ls.FastM(None, nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico", L=1.5 * n * h, Lp=4.0 * n * h)
+    t_op = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cache = S.entriesSparseAConv(k, X, Y, M, n, n, strict=False)
+    As = S.buildSparseAConv(k, X, Y, M, n, n, strict=False, _cache=cache)
+    AG = S.buildSparseAGConv(k, X, Y, M, n, n, strict=False, _cache=cache)
+    Msp = (As + k ** 2 * (AG @ sp.diags(nu))).tocsc()
+    t_sp = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Pl = ls.SparsifyingPreconditioner(Msp, As, solverType="GPU", grid=(n, n))
+    t_fac = time.perf_counter() - t0
+    u_inc = np.exp(1j * k * X)
+    rhs = -(M * u_inc - u_inc)                                 # plasma_example.jl:160-161
+    db = ls.DeviceBuffer.from_host(rhs)
+    ws = ls.KrylovWorkspace(N)
+    dx = ls.DeviceBuffer.from_host(np.zeros(N, complex))
+    ls.gmres_(dx, M, db, Pl=Pl, reltol=1e-8, maxiter=3, workspace=ws)      # warm-up
+    dx = ls.DeviceBuffer.from_host(np.zeros(N, complex))
+    t0 = time.perf_counter()
+    _, hist = ls.gmres_(dx, M, db, Pl=Pl, reltol=1e-8, maxiter=args.gmres_maxiter, log=True, workspace=ws)
+    dt = time.perf_counter() - t0
+    u = dx.to_host()
+    true_res = float(np.linalg.norm((M * u) - rhs) / np.linalg.norm(rhs))
+    # the Msp solve alone, device resident
+    F = Pl.MspGPU
+    dv = ls.DeviceBuffer.from_host(rhs)
+    for _ in range(2):
+        F.solve(dv)
+    F.sync(); F.timer_start()
+    for _ in range(5):
+        F.solve(dv)
+    msp_ms = F.timer_stop() / 5
+    its = max(hist.iters, 1)
+    out = {"metric": "gmres_time_to_1e-8 (sparsifying preconditioner, config 3)", "grid": [n, n],
+           "contrast": "plasma profile of tests/plasma_example.jl:53-68 (discontinuous)", "k": k,
+           "time_s": dt, "iters": hist.iters, "converged": hist.isconverged, "restart": 20, "mv_products": hist.mvps,
+           "ms_per_iter": 1e3 * dt / its, "true_rel_residual": true_res,
+           "gpu_loop_s": dt - hist.msp_host_seconds, "msp_solve_s": (hist.mvps) * msp_ms * 1e-3, "msp_solve_ms_each": msp_ms,
+           "pcie_s": 0.0, "msp_host_s": hist.msp_host_seconds,
+           "msp_factor": {"bytes": F.factor_bytes, "depth": F.depth, "seconds": F.factor_seconds, "call_seconds": t_fac,
+                          "solve_GBs": F.factor_bytes / msp_ms / 1e6, "solve_hbm_frac": F.factor_bytes / msp_ms / 1e6 / peak},
+           "setup_s": {"operator": t_op, "sparsifier_matrices": t_sp, "msp_factorisation": t_fac},
+           "note": "Pl = Msp^-1 As entirely on the GPU (ls_gmres_msp): no host work and no PCIe traffic per iteration; "
+                   "msp_solve_s = Msp solves inside the loop x the solve's own CUDA-event time"}
+    if args.precond_host and n <= 1024:
+        Ph = ls.SparsifyingPreconditioner(Msp, As)              # host SuperLU through the ls_solve_cb callback
+        dx = ls.DeviceBuffer.from_host(np.zeros(N, complex))
+        t0 = time.perf_counter()
+        _, hh = ls.gmres_(dx, M, db, Pl=Ph, reltol=1e-8, maxiter=args.gmres_maxiter, log=True, workspace=ws)
+        dth = time.perf_counter() - t0
+        out["host_callback_route"] = {"time_s": dth, "iters": hh.iters, "gpu_loop_s": dth - hh.msp_host_seconds,
+                                      "msp_solve_plus_pcie_s": hh.msp_host_seconds,
+                                      "hist_rel_vs_device": float(np.max(np.abs(hh["resnorm"] - hist["resnorm"]) / hist["resnorm"])) if hh.iters == hist.iters else None}
+        Ph.destroy()
+    Pl.destroy()
+    M.destroy()
+    return out
 
 
 def bench_krylov_kernels(ls, n, peak):
@@ -311,9 +577,13 @@ def bench_krylov_kernels(ls, n, peak):
         for _ in range(20):
             G.mv(x, y)
         ms = G.timer_stop() / 20
-        alg = A.nnz * 20 + 4 * (N + 1) + 32 * N
-        out["spmv_" + name] = {"format": G.format, "nnz": int(A.nnz), "ms": ms, "csr_accounting_bytes": alg,
-                               "GBs": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+        # bytes the format as stored has to move: CSR = values 16 + int32 column 4 per nonzero + row pointers + x, y;
+        # stencil classes = 1 class byte + x (16) + y (16) per row
+        fmt_bytes = (A.nnz * 20 + 4 * (N + 1) + 32 * N) if G.format == "csr" else 33 * N
+        out["spmv_" + name] = {"format": G.format, "nnz": int(A.nnz), "ms": ms, "bytes": fmt_bytes,
+                               "bytes_model": "CSR: 20 nnz + 4 (N+1) + 32 N" if G.format == "csr" else "stencil classes: 33 N",
+                               "GBs": fmt_bytes / ms / 1e6, "hbm_frac": fmt_bytes / ms / 1e6 / peak,
+                               "csr_equivalent_GBs": (A.nnz * 20 + 4 * (N + 1) + 32 * N) / ms / 1e6}
         G.destroy()
     ws = ls.KrylovWorkspace(N)
     for kk in (10, 20):
@@ -324,7 +594,7 @@ def bench_krylov_kernels(ls, n, peak):
             ws.mgs_step(V, N, kk, y)
         ms = ws.timer_stop() / 10
         alg = (64 * kk + 48 + 32) * N
-        out["mgs_k%d" % kk] = {"ms": ms, "algorithmic_bytes": alg, "GBs": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+        out["mgs_k%d" % kk] = {"ms": ms, "bytes": alg, "GBs": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / peak}
         V.free()
     return out
 
@@ -337,9 +607,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=2048, help="2-D grid side")
     ap.add_argument("--n3", type=int, default=256, help="3-D grid side")
+    ap.add_argument("--n3-large", type=int, default=512, help="second 3-D grid (config 5's size); 0 skips it")
+    ap.add_argument("--precond-n", type=int, default=2048, help="grid side of the preconditioned solve (config 3)")
+    ap.add_argument("--precond-host", action="store_true", help="also time the host-callback (SuperLU) route, n <= 1024")
     ap.add_argument("--gmres-maxiter", type=int, default=1000)
+    ap.add_argument("--gmres3d-maxiter", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the 3-D and GMRES sections")
+    ap.add_argument("--no-extras", action="store_true", help="skip everything but the headline apply")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -356,7 +631,7 @@ def main():
     import fast_solver_lippmann_schwinger_b200 as ls
     from fast_solver_lippmann_schwinger_b200 import dist as lsd
     from fast_solver_lippmann_schwinger_b200._lib import check, lib
-    from fast_solver_lippmann_schwinger_b200.problems import gv_problem_2d
+    from fast_solver_lippmann_schwinger_b200.problems import nu_gaussian_2d
 
     dist = None
     if world > 1:
@@ -366,12 +641,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     check(lib().ls_set_device(local_rank))
     peak, peak_src = measured_peaks()
+    counters = ncu_counters()
 
     n = args.n
     N = n * n
-    nu, gfft, k, h = gv_problem_2d(n)
-    M = ls.FastM(gfft, nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico")
-    del gfft
+    # contrast on the host; the Greengard-Vico spectrum is evaluated on the device (ls_op2d_create_gv, L and Lp as
+    # buildFastConvolution takes them, FastConvolution.jl:187-188)
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    xg = -0.5 + h * np.arange(n)
+    nu = nu_gaussian_2d(np.repeat(xg[:, None], n, axis=1).reshape(-1, order="F"), np.repeat(xg[None, :], n, axis=0).reshape(-1, order="F"))
+    t_create = time.perf_counter()
+    M = ls.FastM(None, nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico", L=1.5 * n * h, Lp=4.0 * n * h)
+    t_create = time.perf_counter() - t_create
     rng = np.random.default_rng(1234 + rank)
     b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
     db = ls.DeviceBuffer.from_host(b)
@@ -402,6 +684,14 @@ def main():
     phase_ms, phase_cnt = M.profile_read(3)
     M.profile_enable(False)
     launches = M.launch_count() - launches0
+    # the timed region lasts milliseconds, an nvidia-smi query ~0.1 s: keep the GPU under the same load (untimed applies)
+    # for ~1.5 s so that the sampler sees the clocks / throttle reasons this workload runs at
+    if rank == 0:
+        t_soak = time.perf_counter()
+        while time.perf_counter() - t_soak < 1.5:
+            for _ in range(200):
+                M.mul_(dy, db)
+            M.sync()
 
     # ---- end to end through the public host API (pinned host buffers) -----------------------
     hb = ls.PinnedArray((N,))
@@ -416,6 +706,9 @@ def main():
         ls.fastconvolution(M, hb.array, out=hy.array)    # H2D b, 3 kernels, D2H y, synchronous
     e2e_s = time.perf_counter() - t0
     checksum = float(np.abs(hy.array).sum())
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed steps + 1.5 s of the same applies (untimed) + the e2e steps"
 
     # ---- max over ranks ---------------------------------------------------------------
     if dist is not None:
@@ -426,26 +719,54 @@ def main():
 
     extras = {}
     if not args.no_extras:
+        if rank == 0:
+            extras["device_peaks"] = device_peaks(lib())
         if rank == 0 and world == 1:
             extras["gmres"] = bench_gmres(args, ls, M, n, k, h, peak)
             extras["krylov_kernels"] = bench_krylov_kernels(ls, n, peak)
         barrier()
         M.destroy()
-        del db, dy
-        extras["apply3d"] = bench_3d(args, ls, lsd, rank, world, local_rank, dist, peak, peak_src)
-    clocks = sampler.stop() if rank == 0 else None
+        db.free(); dy.free()
+        if rank == 0 and world == 1 and args.precond_n > 0:
+            try:
+                extras["gmres_precond"] = bench_gmres_precond(args, ls, peak)
+            except Exception as ex:            # report, never hide: the headline line must still be printed
+                extras["gmres_precond"] = {"error": repr(ex)}
+        if not args.no_parity:
+            extras["parity"] = parity_block(ls, lsd, rank, world, dist)
+        extras["apply3d"] = bench_3d(args, args.n3, ls, lsd, rank, world, dist, peak, peak_src, counters)
+        if args.n3_large:
+            extras["apply3d_%d" % args.n3_large] = bench_3d(args, args.n3_large, ls, lsd, rank, world, dist, peak, peak_src, counters)
+            try:
+                extras["gmres3d_%d" % args.n3_large] = bench_gmres3d(args, args.n3_large, ls, lsd, rank, world, dist)
+            except Exception as ex:
+                if world > 1:
+                    raise                  # a rank that drops out of a collective would hang the others: fail loudly
+                extras["gmres3d_%d" % args.n3_large] = {"error": repr(ex)}
 
     if rank == 0:
         value = world * args.steps / (ms * 1e-3)
         p2_ms = phase_ms[1] / max(phase_cnt[1], 1)
-        # SURVEY.md 8(d) accounting of the literal pruned-4x pass structure: P2 = A read 64N + spectrum 256N + C write 64N.
-        # The handle runs the same operator with 2x padding (kernel restricted to the needed lags): P2 moves 32N + 64N + 32N.
-        alg_bytes_p2 = 384.0 * N
-        impl_bytes_p2 = 128.0 * N
-        achieved = alg_bytes_p2 / (p2_ms * 1e-3) / 1e9
+        ms_step = ms / args.steps
+        # P2 as implemented (2x compact padding): input slab 32N + spectrum 64N + output slab 32N per launch.
+        bytes_p2 = 128.0 * N
+        achieved = bytes_p2 / (p2_ms * 1e-3) / 1e9
+        c2 = counters.get("p2_%d" % n, {})
+        roof = {"bound": "hbm", "kernel": "k_mid_swap (P2: per padded row, 2 x (forward FFT, spectrum multiply, inverse FFT), combined)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "bytes_per_launch": bytes_p2, "bytes_model": "implemented pass, 2x compact padding: 32N in + 64N spectrum + 32N out",
+                "traffic": c2.get("dram_bytes"), "traffic_source": c2.get("source"),
+                "peak_source": peak_src, "launch_ms": p2_ms,
+                "survey_model_bytes_per_launch": 384.0 * N,
+                "survey_model_note": "SURVEY.md 8(d) counts the literal pruned-4x pass (384 N); the implemented pass needs a third of it, so that figure is not a roofline fraction"}
+        dp = extras.get("device_peaks")
+        if dp and c2.get("fp64_lane_instr"):
+            roof["fp64"] = {"lane_instr_per_launch": c2["fp64_lane_instr"], "peak_tera_lane_instr_per_s": dp["fp64_add_tera_lane_instr_per_s"],
+                            "frac": c2["fp64_lane_instr"] / (p2_ms * 1e-3) / 1e12 / dp["fp64_add_tera_lane_instr_per_s"],
+                            "note": "FP64 instructions of the pass (ncu, DADD + DMUL + DFMA lanes) against the measured FP64 issue rate"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(n),
             "e2e": {"value": world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * N,
@@ -454,22 +775,15 @@ def main():
             "clocks": clocks,
             "evaluation": "pruned FFTs with 2x padding on the kernel restricted to the lags the cropped apply touches "
                           "(same operator as the reference's 4x-padded evaluation to 1e-16; LS_FLAG_PAD4 keeps the literal one)",
-            "roofline": {"bound": "hbm", "kernel": "k_mid_fused (P2: per padded row, 2 x (forward FFT, spectrum multiply, inverse FFT), accumulated)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "algorithmic_bytes_model": "SURVEY.md 8(d), literal pruned-4x pass structure (frac > 1: the implemented 2x-padded pass needs a third of these bytes)",
-                         "implemented_bytes_per_launch": impl_bytes_p2, "implemented_achieved": impl_bytes_p2 / (p2_ms * 1e-3) / 1e9,
-                         "implemented_frac": impl_bytes_p2 / (p2_ms * 1e-3) / 1e9 / peak,
-                         "traffic": (0.4027e9 + 0.1126e9) if n == 2048 else None,
-                         "traffic_source": "ncu --set full r1_j at 2048^2: dram read 0.403 GB + write 0.113 GB per launch (profiles/r1_j_2d_2048_kernel0.txt)",
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_p2, "launch_ms": p2_ms},
-            "apply_roofline": {"survey_bytes_per_apply": 568.0 * N, "survey_achieved": 568.0 * N / (ms / args.steps * 1e-3) / 1e9,
-                               "survey_frac": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak,
-                               "survey_frac_of_nominal_8TBs": 568.0 * N / (ms / args.steps * 1e-3) / 1e9 / 8000.0,
-                               "implemented_bytes_per_apply": 248.0 * N,
-                               "implemented_frac": 248.0 * N / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "roofline": roof,
+            "apply_roofline": {"bytes_per_apply": 248.0 * N, "achieved": 248.0 * N / (ms_step * 1e-3) / 1e9,
+                               "frac": 248.0 * N / (ms_step * 1e-3) / 1e9 / peak,
+                               "survey_model_bytes_per_apply": 568.0 * N,
+                               "survey_model_time_ratio": 568.0 * N / peak / 1e9 / (ms_step * 1e-3)},
             "phase_ms": {"P1_fwd_columns": phase_ms[0] / max(phase_cnt[0], 1), "P2_fused_rows": p2_ms,
                          "P3_inv_columns": phase_ms[2] / max(phase_cnt[2], 1)},
             "checksum": checksum,
+            "operator_create_s": t_create,
         }
         line.update(extras)
         if not args.no_cpu_baseline:

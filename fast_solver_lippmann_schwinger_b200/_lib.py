@@ -81,9 +81,11 @@ def lib():
         "ls_host_alloc_pinned": (ci, [C.POINTER(vp), C.c_size_t]),
         "ls_host_free_pinned": (ci, [vp]),
         "ls_op2d_create": (ci, [C.POINTER(vp), i64, i64, i64, i64, vp, vp, dbl, ci, ci]),
+        "ls_op2d_create_gv": (ci, [C.POINTER(vp), i64, i64, vp, dbl, dbl, dbl, ci]),
         "ls_op2d_apply": (ci, [vp, vp, vp, ci, ci]),
         "ls_op3d_create": (ci, [C.POINTER(vp), i64, i64, i64, i64, i64, i64, vp, vp, dbl, dbl, dbl, ci]),
         "ls_op3d_apply": (ci, [vp, vp, vp, ci, ci]),
+        "ls_op3d_info": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
         "ls_nccl_unique_id": (ci, [vp]),
         "ls_op3d_create_dist": (ci, [C.POINTER(vp), i64, i64, i64, vp, dbl, dbl, dbl, ci, ci, vp, ci]),
         "ls_op_size": (ci, [vp, C.POINTER(i64)]),
@@ -114,6 +116,7 @@ def lib():
         "ls_profile_enable": (ci, [vp, ci]),
         "ls_profile_read": (ci, [vp, C.POINTER(dbl), C.POINTER(i64), ci]),
         "ls_test_fft_lines": (ci, [i64, i64, vp, vp, ci]),
+        "ls_test_device_peaks": (ci, [C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

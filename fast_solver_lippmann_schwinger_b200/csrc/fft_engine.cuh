@@ -322,6 +322,43 @@ __device__ __forceinline__ void demod_accumulate_block(cd* acc, const cd* v, int
 }
 
 // middle / last stages ------------------------------------------------------------------
+// Middle-stage twiddles w^d, d = 1..R-1, w = w_{Mprev}^b.  LS_TW_TABLE: every factor read from the shared-memory
+// table (R-1 LDS.128 per butterfly - a fifth of the engine's shared-memory traffic at N = 2048).  Default: only w is
+// read, the powers come from a product tree of depth <= 4 (w2 = w^2, w4 = w2^2, w8 = w4^2, the rest one product of
+// two of those), about 4 ulp instead of the table's 0.5 ulp - still four orders below the 1e-12 parity bar - and
+// FP64 work on the otherwise idle per-quadrant pipe instead of wavefronts on the SM-wide shared-memory pipe.
+template <int R, bool CONJ>
+__device__ __forceinline__ void mul_twiddle_powers(cd* v, const cd w1) {
+    auto ap = [](cd a, cd w) { return CONJ ? cmulc(a, w) : cmul(a, w); };
+    const cd w2 = cmul(w1, w1);
+    const cd w4 = cmul(w2, w2);
+    if constexpr (R == 16) {
+        const cd w8 = cmul(w4, w4);
+        v[8] = ap(v[8], w8);
+        v[1] = ap(v[1], w1);  v[9] = ap(v[9], cmul(w8, w1));
+        v[2] = ap(v[2], w2);  v[10] = ap(v[10], cmul(w8, w2));
+        const cd w3 = cmul(w2, w1);
+        v[3] = ap(v[3], w3);  v[11] = ap(v[11], cmul(w8, w3));
+        v[4] = ap(v[4], w4);  v[12] = ap(v[12], cmul(w8, w4));
+        const cd w5 = cmul(w4, w1);
+        v[5] = ap(v[5], w5);  v[13] = ap(v[13], cmul(w8, w5));
+        const cd w6 = cmul(w4, w2);
+        v[6] = ap(v[6], w6);  v[14] = ap(v[14], cmul(w8, w6));
+        const cd w7 = cmul(w4, w3);
+        v[7] = ap(v[7], w7);  v[15] = ap(v[15], cmul(w8, w7));
+    } else {
+        static_assert(R == 8, "middle stages are radix 8 or 16");
+        v[1] = ap(v[1], w1);
+        v[2] = ap(v[2], w2);
+        const cd w3 = cmul(w2, w1);
+        v[3] = ap(v[3], w3);
+        v[4] = ap(v[4], w4);
+        v[5] = ap(v[5], cmul(w4, w1));
+        v[6] = ap(v[6], cmul(w4, w2));
+        v[7] = ap(v[7], cmul(w4, w3));
+    }
+}
+
 template <int N, int I>
 __device__ __forceinline__ void fwd_stage(cd* v, int t, const TwState<N>& tw) {
     typedef Stage<N, I> St;
@@ -330,8 +367,12 @@ __device__ __forceinline__ void fwd_stage(cd* v, int t, const TwState<N>& tw) {
         dftR<-1, St::R>(v + u * St::R);
         if (!St::LAST) {
             int b = St::bidx(t, u);
+#ifdef LS_TW_TABLE
 #pragma unroll
             for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmul(v[u * St::R + d], tw.tw1[d * St::M + b]);
+#else
+            mul_twiddle_powers<St::R, false>(v + u * St::R, tw.tw1[St::M + b]);
+#endif
         }
     }
 }
@@ -342,8 +383,12 @@ __device__ __forceinline__ void inv_stage(cd* v, int t, const TwState<N>& tw) {
     for (int u = 0; u < St::NB; ++u) {
         if (!St::LAST) {
             int b = St::bidx(t, u);
+#ifdef LS_TW_TABLE
 #pragma unroll
             for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmulc(v[u * St::R + d], tw.tw1[d * St::M + b]);
+#else
+            mul_twiddle_powers<St::R, true>(v + u * St::R, tw.tw1[St::M + b]);
+#endif
         }
         dftR<+1, St::R>(v + u * St::R);
     }

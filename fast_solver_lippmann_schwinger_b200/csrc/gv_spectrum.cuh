@@ -9,6 +9,9 @@ namespace ls {
 
 __device__ __forceinline__ lsfft::cd gtrunc3d_eval(double s, double L, double k, double eLk_re, double eLk_im) {
     const double PI = 3.141592653589793;
+    // Q7: removable singularity at s == k (Functions.jl:50 divides by k^2 - s^2); a grid frequency that hits k exactly is
+    // moved by sqrt(eps) relative instead of producing NaN
+    if (s == k) s = k * (1.0 + 1.4901161193847656e-08);
     const double Ls = L * s;
     const double c = cos(Ls);
     double sinc;

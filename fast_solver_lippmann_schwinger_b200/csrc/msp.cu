@@ -91,22 +91,30 @@ struct GemvArgs {
     cd* out; long ostride; const int* oidx; cd* og;
 };
 
-template <int LANES>
+// One group of LANES lanes handles UNR consecutive rows of one node: UNR independent 16-byte loads per lane and
+// column step are in flight before the first multiply (the kernels are pure streaming: with one row per group a warp
+// had 512 bytes outstanding and the sweep ran at 30 % of the HBM peak), and x is fetched once per UNR rows.
+template <int LANES, int UNR>
 __global__ void __launch_bounds__(256)
-k_msp_gemv(const GemvArgs a) {
-    const long task = ((long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+k_msp_gemv(const GemvArgs a, unsigned rblocks, unsigned ngroups) {
+    const unsigned g = (blockIdx.x * 256u + threadIdx.x) / LANES;
     const int lane = threadIdx.x % LANES;
-    const bool live = task < a.ntasks;
-    const long t = live ? task / a.rows : 0;
-    const int r = live ? (int)(task % a.rows) : 0;
-    double sr = 0.0, si = 0.0;
+    const bool live = g < ngroups;
+    const unsigned t = live ? g / rblocks : 0u;
+    const int r0 = live ? (int)(g - t * rblocks) * UNR : 0;
+    double sr[UNR], si[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) { sr[u] = 0.0; si[u] = 0.0; }
     if (live) {
-        const cd* row = a.M + (t * a.rows + r) * (long)a.cols;
-        const cd* xv = a.x ? a.x + t * a.xstride : nullptr;
-        const int* xi = a.xidx ? a.xidx + t * (long)a.cols : nullptr;
-#pragma unroll 4
+        const cd* base = a.M + ((long)t * a.rows + r0) * (long)a.cols;
+        const cd* xv = a.x ? a.x + (long)t * a.xstride : nullptr;
+        const int* xi = a.xidx ? a.xidx + (long)t * a.cols : nullptr;
+        const int nrow = min(UNR, a.rows - r0);
+#pragma unroll 2
         for (int c = lane; c < a.cols; c += LANES) {
-            const cd m = __ldg(&row[c]);
+            cd m[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) m[u] = (u < nrow) ? __ldg(&base[(long)u * a.cols + c]) : make_double2(0.0, 0.0);
             cd v;
             if (xi) {
                 const int gi = __ldg(&xi[c]);
@@ -114,38 +122,55 @@ k_msp_gemv(const GemvArgs a) {
             } else {
                 v = xv[c];
             }
-            sr += m.x * v.x - m.y * v.y;
-            si += m.x * v.y + m.y * v.x;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                sr[u] += m[u].x * v.x - m[u].y * v.y;
+                si[u] += m[u].x * v.y + m[u].y * v.x;
+            }
         }
     }
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-        sr += __shfl_xor_sync(0xffffffffu, sr, o, LANES);
-        si += __shfl_xor_sync(0xffffffffu, si, o, LANES);
-    }
-    if (live && lane == 0) {
-        cd val = make_double2(a.sign * sr, a.sign * si);
-        if (a.y0) { const cd y = a.y0[t * a.y0stride + r]; val.x += y.x; val.y += y.y; }
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            sr[u] += __shfl_xor_sync(0xffffffffu, sr[u], o, LANES);
+            si[u] += __shfl_xor_sync(0xffffffffu, si[u], o, LANES);
+        }
+    if (live && lane < UNR && r0 + lane < a.rows) {
+        const int r = r0 + lane;
+        double vr = 0.0, vi = 0.0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) if (u == lane) { vr = sr[u]; vi = si[u]; }
+        cd val = make_double2(a.sign * vr, a.sign * vi);
+        if (a.y0) { const cd y = a.y0[(long)t * a.y0stride + r]; val.x += y.x; val.y += y.y; }
         if (a.oidx) {
-            const int gi = a.oidx[t * (long)a.rows + r];
+            const int gi = a.oidx[(long)t * a.rows + r];
             if (gi >= 0) a.og[gi] = val;
         } else {
-            a.out[t * a.ostride + r] = val;
+            a.out[(long)t * a.ostride + r] = val;
         }
     }
 }
 
 int launch_gemv(const GemvArgs& a, cudaStream_t s) {
     if (a.ntasks <= 0) return LS_OK;
+    constexpr int UNR = 4;
+    // lanes per row group: about `cpl` column steps per lane - the cross-lane reduction costs 4 log2(lanes) shuffles per
+    // row, which dominates the small blocks when every lane owns a single column (measured: 16 x 16 leaf blocks)
+    static int cpl = -1;
+    if (cpl < 0) { const char* e = getenv("LS_MSP_COLS_PER_LANE"); cpl = e ? atoi(e) : 8; if (cpl < 1) cpl = 1; }
     int lanes = 4;
-    while (lanes < 32 && lanes * 2 <= a.cols) lanes *= 2;       // about two or more columns per lane
-    const long threads = a.ntasks * lanes;
+    while (lanes < 32 && lanes * cpl < a.cols) lanes *= 2;
+    const unsigned rblocks = (unsigned)((a.rows + UNR - 1) / UNR);
+    const long nodes = a.ntasks / a.rows;
+    const long ngroups = nodes * rblocks;
+    const long threads = ngroups * lanes;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
     switch (lanes) {
-        case 4:  k_msp_gemv<4><<<blocks, 256, 0, s>>>(a); break;
-        case 8:  k_msp_gemv<8><<<blocks, 256, 0, s>>>(a); break;
-        case 16: k_msp_gemv<16><<<blocks, 256, 0, s>>>(a); break;
-        default: k_msp_gemv<32><<<blocks, 256, 0, s>>>(a); break;
+        case 4:  k_msp_gemv<4, UNR><<<blocks, 256, 0, s>>>(a, rblocks, (unsigned)ngroups); break;
+        case 8:  k_msp_gemv<8, UNR><<<blocks, 256, 0, s>>>(a, rblocks, (unsigned)ngroups); break;
+        case 16: k_msp_gemv<16, UNR><<<blocks, 256, 0, s>>>(a, rblocks, (unsigned)ngroups); break;
+        default: k_msp_gemv<32, UNR><<<blocks, 256, 0, s>>>(a, rblocks, (unsigned)ngroups); break;
     }
     return LS_OK;
 }

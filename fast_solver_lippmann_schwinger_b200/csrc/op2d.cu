@@ -17,6 +17,7 @@
 #include "ls_common.cuh"
 #include "op2d_base.cuh"
 #include "line_kernels.cuh"
+#include "gv_spectrum2d.cuh"
 #ifdef LS_EXPERIMENTS
 #include "line_kernels_experiments.cuh"   // measured-and-rejected variants: only with -DLS_EXPERIMENTS (profiles/r1_b_notes.md)
 #endif
@@ -60,6 +61,28 @@ __global__ void k_permute_g2d(const cd* __restrict__ gin, cd* __restrict__ gout,
     long ix = (kx + ne / 2) % ne, iy = (ky + me / 2) % me;
     cd v = gin[ix + ne * iy];
     gout[idx] = make_double2(v.x * scale, v.y * scale);
+}
+
+// same layout as k_permute_g2d, values evaluated on the device (Gtruncated2D, Functions.jl:40-42) instead of gathered
+__global__ void k_fill_g2d(cd* __restrict__ gout, const int* __restrict__ fx, const int* __restrict__ fy,
+                           long n, long m, long ne, long me, double scale, Gv2dParams p) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = ne * me;
+    if (idx >= total) return;
+    long sy = idx % m;
+    long ry = (idx / m) % 4;
+    long sx = idx / (4 * m);
+    long kx = 4L * fx[sx % n] + sx / n;
+    long ky = 4L * fy[sy] + ry;
+    long ix = (kx + ne / 2) % ne, iy = (ky + me / 2) % me;
+    cd v = gtrunc2d_eval(p, ix, iy, ne, me);
+    gout[idx] = make_double2(v.x * scale, v.y * scale);
+}
+// the centred ne x me array exactly as the reference holds it (general-size path)
+__global__ void k_fill_g2d_centred(cd* __restrict__ gout, long ne, long me, Gv2dParams p) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ne * me) return;
+    gout[idx] = gtrunc2d_eval(p, idx % ne, idx / ne, ne, me);
 }
 
 template <int N> int launch_fwd(Op2D* op, const cd* b, const double* nu) {
@@ -115,12 +138,17 @@ template <int N> int launch_mid_swap_op(Op2D* op) {
     la.nr = 2;
     static int gl = -1, minb = -1;   // LS_P2_GLOAD: 0 spectrum held in registers across the last stage, 1 L2 prefetch + load at the multiply
     if (gl < 0) { const char* e = getenv("LS_P2_GLOAD"); gl = e ? atoi(e) : 0; }
-    if (minb < 0) { const char* e = getenv("LS_P2_MINB"); minb = e ? atoi(e) : 3; }
+    // CTAs per SM (128-thread CTAs).  Measured on B200 (profiles/r2_e_notes.md): at N >= 1024 three CTAs are slower than two
+    // (168-register cap -> spills, and 3 x 66 KB of shared memory leaves 30 KB of L1 for the strided line loads:
+    // 2048^2 0.297 vs 0.211 ms); at N <= 512 several lines share a CTA and three CTAs win (512^2 0.0189 vs 0.0194 ms).
+    if (minb < 0) { const char* e = getenv("LS_P2_MINB"); minb = e ? atoi(e) : 0; }
+    const int use_minb = minb ? minb : (N <= 512 ? 3 : 2);
     constexpr int MB = (GeoA<N>::THREADS <= 128 ? 3 : 1);
     op->phase_begin(1);
     cudaError_t e;
-    if (minb == 2 && MB == 3) e = gl ? lsk::launch_mid_swap<N, 2, 1>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la)
-                                     : lsk::launch_mid_swap<N, 2, 0>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la);
+    constexpr int MB2 = (MB == 3 ? 2 : 1);      // 128-thread CTAs: two per SM by default (255 registers, no spills)
+    if (use_minb == 2 || MB == 1) e = gl ? lsk::launch_mid_swap<N, MB2, 1>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la)
+                                     : lsk::launch_mid_swap<N, MB2, 0>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la);
     else e = gl ? lsk::launch_mid_swap<N, MB, 1>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la)
                 : lsk::launch_mid_swap<N, MB, 0>(op->stream, op->pn, op->d_A, op->d_C, op->d_G, op->d_TABm, la);
     op->phase_end();
@@ -310,9 +338,25 @@ int compact_spectrum(Op2D* op, cd* g4s) {
 
 extern "C" {
 
+static int op2d_create_impl(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
+                            const double* nu, const ls_cdouble* gfft, double omega, int quadrule, int flags,
+                            double L, double Lp);
+
 int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
                    const double* nu, const ls_cdouble* gfft, double omega, int quadrule, int flags) {
     LS_REQUIRE(out && nu && gfft, LS_ERR_INVALID, "ls_op2d_create: null pointer");
+    return op2d_create_impl(out, n, m, ne, me, nu, gfft, omega, quadrule, flags, 0.0, 0.0);
+}
+
+int ls_op2d_create_gv(ls_handle* out, int64_t n, int64_t m, const double* nu, double omega, double L, double Lp, int flags) {
+    LS_REQUIRE(out && nu, LS_ERR_INVALID, "ls_op2d_create_gv: null pointer");
+    LS_REQUIRE(L > 0 && Lp > 0 && omega > 0, LS_ERR_INVALID, "ls_op2d_create_gv: L, Lp and k must be positive");
+    return op2d_create_impl(out, n, m, 4 * n, 4 * m, nu, nullptr, omega, LS_QUAD_GREENGARD_VICO, flags, L, Lp);
+}
+
+static int op2d_create_impl(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
+                            const double* nu, const ls_cdouble* gfft, double omega, int quadrule, int flags,
+                            double L, double Lp) {
     LS_REQUIRE(n > 0 && m > 0 && ne > 0 && me > 0, LS_ERR_INVALID, "ls_op2d_create: non-positive size");
     LS_REQUIRE(quadrule == LS_QUAD_TRAPEZOIDAL || quadrule == LS_QUAD_GREENGARD_VICO, LS_ERR_INVALID,
                "ls_op2d_create: unknown quadRule %d", quadrule);
@@ -323,8 +367,21 @@ int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
     }
     LS_REQUIRE(ne == 4 * n && me == 4 * m, LS_ERR_INVALID,
                "ls_op2d_create: Greengard_Vico needs ne = 4n, me = 4m (FastConvolution.jl:201)");
-    if (!(fft_size_supported(n) && fft_size_supported(m)) || (flags & LS_FLAG_FORCE_GENERIC))
-        return create_op2d_generic(out, n, m, ne, me, nu, gfft, omega, quadrule);
+    if (!(fft_size_supported(n) && fft_size_supported(m)) || (flags & LS_FLAG_FORCE_GENERIC)) {
+        if (gfft) return create_op2d_generic(out, n, m, ne, me, nu, gfft, omega, quadrule);
+        // general-size path with the spectrum generated on the device: the centred array as the reference holds it
+        LS_REQUIRE(ne + n - 1 <= 4096 && me + m - 1 <= 4096, LS_ERR_UNSUPPORTED,
+                   "ls_op2d_create_gv: n=%ld, m=%ld: the general-size GPU path serves 5n - 1 <= 4096", (long)n, (long)m);
+        cd* d_g = nullptr;
+        LS_CUDA_TRY(cudaMalloc((void**)&d_g, (size_t)ne * me * sizeof(cd)));
+        const Gv2dParams gp = gv2d_params(L, Lp, omega);
+        k_fill_g2d_centred<<<(unsigned)(((size_t)ne * me + 255) / 256), 256>>>(d_g, ne, me, gp);
+        cudaError_t ge = cudaDeviceSynchronize();
+        int grc = ge == cudaSuccess ? create_op2d_generic(out, n, m, ne, me, nu, nullptr, omega, quadrule, d_g) : LS_ERR_CUDA;
+        if (ge != cudaSuccess) set_error("spectrum generation failed: %s", cudaGetErrorString(ge));
+        cudaFree(d_g);
+        return grc;
+    }
 
     Op2D* op = new Op2D();
     int rc = op->init_base(KIND_OP2D);
@@ -345,14 +402,21 @@ int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
         cd* d_gin = nullptr;
         TRY(op->dupload((void**)&d_fx, fx.data(), fx.size() * sizeof(int)));
         TRY(op->dupload((void**)&d_fy, fy.data(), fy.size() * sizeof(int)));
-        TRY(op->dupload((void**)&d_gin, gfft, NE * sizeof(cd)));
         TRY(op->dmalloc((void**)&op->d_G, NE * sizeof(cd)));
         const int th = 256;
-        k_permute_g2d<<<(unsigned)((NE + th - 1) / th), th, 0, op->stream>>>(
-            d_gin, op->d_G, d_fx, d_fy, n, m, ne, me, 1.0 / ((double)ne * (double)me));
+        if (gfft) {
+            TRY(op->dupload((void**)&d_gin, gfft, NE * sizeof(cd)));
+            k_permute_g2d<<<(unsigned)((NE + th - 1) / th), th, 0, op->stream>>>(
+                d_gin, op->d_G, d_fx, d_fy, n, m, ne, me, 1.0 / ((double)ne * (double)me));
+        } else {
+            // Gtruncated2D evaluated straight into the kernel layout: no host Bessel evaluation, no 16 ne me byte upload
+            k_fill_g2d<<<(unsigned)((NE + th - 1) / th), th, 0, op->stream>>>(
+                op->d_G, d_fx, d_fy, n, m, ne, me, 1.0 / ((double)ne * (double)me), gv2d_params(L, Lp, omega));
+        }
         cudaError_t e = cudaStreamSynchronize(op->stream);
-        if (e != cudaSuccess) { set_error("spectrum permutation failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
-        op->dfree(d_gin); op->dfree(d_fx); op->dfree(d_fy);
+        if (e != cudaSuccess) { set_error("spectrum set-up failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
+        if (d_gin) op->dfree(d_gin);
+        op->dfree(d_fx); op->dfree(d_fy);
     }
     op->nr = 4;
     if (!(flags & LS_FLAG_PAD4)) {

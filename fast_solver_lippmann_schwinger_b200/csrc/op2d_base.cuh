@@ -15,7 +15,8 @@ struct Op2DBase : HandleBase {
 
 // general sizes / trapezoidal rule: line DFTs of arbitrary length by Bluestein's algorithm on the
 // power-of-two engine.  Returns LS_ERR_UNSUPPORTED when a padded line does not fit the engine.
+// gfft: host array in the reference's layout, or nullptr with gfft_dev = the same array already on the device.
 int create_op2d_generic(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me, const double* nu,
-                        const ls_cdouble* gfft, double omega, int quadrule);
+                        const ls_cdouble* gfft, double omega, int quadrule, const cd* gfft_dev = nullptr);
 
 }  // namespace ls

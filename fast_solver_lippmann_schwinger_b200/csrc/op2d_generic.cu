@@ -99,7 +99,7 @@ int Op2DGeneric::apply_dev(const cd* b, cd* y, int mode) {
 namespace ls {
 
 int create_op2d_generic(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me, const double* nu,
-                        const ls_cdouble* gfft, double omega, int quadrule) {
+                        const ls_cdouble* gfft, double omega, int quadrule, const cd* gfft_dev) {
     // size check first (no CUDA call needed to refuse)
     LS_REQUIRE(ne + n - 1 <= 4096 && me + m - 1 <= 4096, LS_ERR_UNSUPPORTED,
                "ls_op2d_create: n=%ld, m=%ld (padded %ld x %ld): the general-size GPU path serves ne + n - 1 <= 4096; "
@@ -117,7 +117,8 @@ int create_op2d_generic(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_
     TRY(op->dupload((void**)&op->d_nu, nu, N * sizeof(double)));
     {
         cd* d_gin = nullptr;
-        TRY(op->dupload((void**)&d_gin, gfft, NE * sizeof(cd)));
+        if (gfft_dev) d_gin = const_cast<cd*>(gfft_dev);
+        else TRY(op->dupload((void**)&d_gin, gfft, NE * sizeof(cd)));
         TRY(op->dmalloc((void**)&op->d_G, NE * sizeof(cd)));
         // ifft normalisation 1/(ne me) and the 1/Nb of each of the four circular convolutions
         const double scale = 1.0 / ((double)ne * (double)me) / ((double)op->X.Nb * (double)op->X.Nb)
@@ -127,7 +128,7 @@ int create_op2d_generic(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_
         k_bs_permute_g<<<148 * 8, 256, 0, op->stream>>>(d_gin, op->d_G, ne, me, sx, sy, scale);
         cudaError_t e = cudaStreamSynchronize(op->stream);
         if (e != cudaSuccess) { set_error("spectrum permutation failed: %s", cudaGetErrorString(e)); delete op; return LS_ERR_CUDA; }
-        op->dfree(d_gin);
+        if (!gfft_dev) op->dfree(d_gin);
     }
     TRY(op->dmalloc((void**)&op->d_A, (size_t)ne * m * sizeof(cd)));
     TRY(op->dmalloc((void**)&op->d_C, (size_t)ne * m * sizeof(cd)));

@@ -49,7 +49,14 @@ struct Op3D : HandleBase {
     cd* d_A1T = nullptr;               // re-slabbed: [chunk][nelc x m x l]  (P > 1 only)
     cd* d_A2 = nullptr;                // nelc x pm x l (one chunk, reused)
     cd* d_b = nullptr; cd* d_y = nullptr;
-    cudaStream_t cstream = nullptr;    // high-priority stream of the NCCL exchanges (P > 1)
+    cudaStream_t cstream = nullptr;    // high-priority stream of the exchanges (P > 1)
+    // Copy-engine exchange (default for P > 1): both exchange buffers are exported with cudaIpcGetMemHandle, and a
+    // transpose is P-1 cudaMemcpyAsync pushes of contiguous blocks straight into the peers' receive buffers (DMA
+    // engines over NVLink: no SM, no staging) closed by a one-element all-reduce, after which every push into this
+    // rank's buffer has landed.  LS_OP3D_XCHG=nccl keeps the grouped ncclSend/ncclRecv all-to-all (same bits).
+    bool ce_exchange = false;
+    std::vector<cd*> peerA1, peerA1T;  // rank q's d_A1 / d_A1T mapped into this process (own entries: the local pointers)
+    double* d_bar = nullptr;
     cudaEvent_t evP1 = nullptr, evDone = nullptr;
     std::vector<cudaEvent_t> evIn, evOut;
     int64_t op_size() const override { return n * m * lloc; }
@@ -58,6 +65,13 @@ struct Op3D : HandleBase {
     int dist_rank() const override { return rank; }
     int dist_size() const override { return P; }
     ~Op3D() override {
+        if (stream) cudaStreamSynchronize(stream);
+        if (cstream) cudaStreamSynchronize(cstream);
+        for (int q = 0; q < (int)peerA1.size(); ++q) {
+            if (q == rank) continue;
+            if (peerA1[q]) cudaIpcCloseMemHandle(peerA1[q]);
+            if (peerA1T[q]) cudaIpcCloseMemHandle(peerA1T[q]);
+        }
         if (comm) ncclCommDestroy(comm);
         for (auto ev : evIn) cudaEventDestroy(ev);
         for (auto ev : evOut) cudaEventDestroy(ev);
@@ -134,6 +148,59 @@ int all_to_all(Op3D* op, const cd* send, cd* recv, long blk_elems, cudaStream_t 
     return LS_OK;
 }
 
+// The same all-to-all on the copy engines: block q of `send` goes to block `rank` of rank q's buffer `peer[q]`
+// (offset `off` = chunk base in both); step s pushes to rank (rank + s) % P, so every rank receives from exactly one
+// source per step.  The closing all-reduce is the completion barrier: a rank leaves it only after every rank has
+// entered it, i.e. after every push (stream-ordered before the sender's all-reduce) has completed.
+int exchange_ce(Op3D* op, const cd* send, const std::vector<cd*>& peer, long off, long blk_elems, cudaStream_t on) {
+    const size_t bytes = (size_t)blk_elems * sizeof(cd);
+    for (int st = 0; st < op->P; ++st) {
+        const int q = (op->rank + st) % op->P;
+        LS_CUDA_TRY(cudaMemcpyAsync(peer[q] + off + (long)op->rank * blk_elems, send + off + (long)q * blk_elems, bytes,
+                                    cudaMemcpyDeviceToDevice, on));
+    }
+    ncclResult_t r = ncclAllReduce(op->d_bar, op->d_bar, 1, ncclDouble, ncclSum, op->comm, on);
+    if (r != ncclSuccess) { set_error("exchange barrier failed: %s", ncclGetErrorString(r)); return LS_ERR_NCCL; }
+    return LS_OK;
+}
+
+// maps the peers' exchange buffers into this process (all ranks of one box; handles travel by ncclAllGather)
+int setup_ce_exchange(Op3D* op) {
+    const int P = op->P;
+    struct Pair { cudaIpcMemHandle_t a1, a1t; };
+    static_assert(sizeof(Pair) == 128, "two 64-byte IPC handles");
+    Pair mine;
+    LS_CUDA_TRY(cudaIpcGetMemHandle(&mine.a1, op->d_A1));
+    LS_CUDA_TRY(cudaIpcGetMemHandle(&mine.a1t, op->d_A1T));
+    char *d_send = nullptr, *d_recv = nullptr;
+    int rc;
+    if ((rc = op->dmalloc((void**)&d_send, sizeof(Pair)))) return rc;
+    if ((rc = op->dmalloc((void**)&d_recv, sizeof(Pair) * P))) return rc;
+    if ((rc = op->dmalloc((void**)&op->d_bar, sizeof(double)))) return rc;
+    LS_CUDA_TRY(cudaMemsetAsync(op->d_bar, 0, sizeof(double), op->stream));
+    LS_CUDA_TRY(cudaMemcpyAsync(d_send, &mine, sizeof(Pair), cudaMemcpyHostToDevice, op->stream));
+    ncclResult_t r = ncclAllGather(d_send, d_recv, sizeof(Pair), ncclChar, op->comm, op->stream);
+    if (r != ncclSuccess) { set_error("IPC handle all-gather failed: %s", ncclGetErrorString(r)); return LS_ERR_NCCL; }
+    std::vector<Pair> all((size_t)P);
+    LS_CUDA_TRY(cudaMemcpyAsync(all.data(), d_recv, sizeof(Pair) * P, cudaMemcpyDeviceToHost, op->stream));
+    LS_CUDA_TRY(cudaStreamSynchronize(op->stream));
+    op->dfree(d_send); op->dfree(d_recv);
+    op->peerA1.assign((size_t)P, nullptr);
+    op->peerA1T.assign((size_t)P, nullptr);
+    op->peerA1[op->rank] = op->d_A1;
+    op->peerA1T[op->rank] = op->d_A1T;
+    for (int q = 0; q < P; ++q) {
+        if (q == op->rank) continue;
+        void *p1 = nullptr, *p2 = nullptr;
+        LS_CUDA_TRY(cudaIpcOpenMemHandle(&p1, all[q].a1, cudaIpcMemLazyEnablePeerAccess));
+        op->peerA1[q] = (cd*)p1;
+        LS_CUDA_TRY(cudaIpcOpenMemHandle(&p2, all[q].a1t, cudaIpcMemLazyEnablePeerAccess));
+        op->peerA1T[q] = (cd*)p2;
+    }
+    op->ce_exchange = true;
+    return LS_OK;
+}
+
 int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
     cudaError_t e = cudaSuccess;
     cudaStream_t s = op->stream, sc = op->cstream;
@@ -161,7 +228,8 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
         LS_CUDA_TRY(cudaStreamWaitEvent(sc, op->evP1, 0));
         for (int c = 0; c < Cx; ++c) {
             op->phase_begin(5, sc);
-            int rc = all_to_all(op, op->d_A1 + c * cstride, op->d_A1T + c * cstride, blk, sc);
+            int rc = op->ce_exchange ? exchange_ce(op, op->d_A1, op->peerA1T, c * cstride, blk, sc)
+                                     : all_to_all(op, op->d_A1 + c * cstride, op->d_A1T + c * cstride, blk, sc);
             op->phase_end(sc);
             if (rc) return rc;
             LS_CUDA_TRY(cudaEventRecord(op->evIn[c], sc));
@@ -218,7 +286,8 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
             LS_CUDA_TRY(cudaEventRecord(op->evOut[c], s));
             LS_CUDA_TRY(cudaStreamWaitEvent(sc, op->evOut[c], 0));
             op->phase_begin(6, sc);
-            int rc = all_to_all(op, op->d_A1T + c * cstride, op->d_A1 + c * cstride, blk, sc);
+            int rc = op->ce_exchange ? exchange_ce(op, op->d_A1T, op->peerA1, c * cstride, blk, sc)
+                                     : all_to_all(op, op->d_A1T + c * cstride, op->d_A1 + c * cstride, blk, sc);
             op->phase_end(sc);
             if (rc) return rc;
         }
@@ -503,6 +572,23 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
             if (ce == cudaSuccess) (c < op->Cx ? op->evIn : op->evOut).push_back(ev);
         }
         if (ce != cudaSuccess) { set_error("exchange stream setup failed: %s", cudaGetErrorString(ce)); delete op; return LS_ERR_CUDA; }
+        const char* xv = getenv("LS_OP3D_XCHG");
+        if (!(xv && strcmp(xv, "nccl") == 0)) {
+            // every rank must take the same route: agree (min over ranks) after the attempt
+            const int ok = setup_ce_exchange(op) == LS_OK ? 1 : 0;
+            cudaGetLastError();
+            int* d_ok = nullptr;
+            TRY(op->dmalloc((void**)&d_ok, sizeof(int)));
+            ce = cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, op->stream);
+            ncclResult_t nr = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, op->comm, op->stream);
+            int all_ok = 0;
+            if (ce == cudaSuccess && nr == ncclSuccess) ce = cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, op->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(op->stream);
+            if (ce != cudaSuccess || nr != ncclSuccess) { set_error("exchange route agreement failed"); delete op; return LS_ERR_NCCL; }
+            op->dfree(d_ok);
+            op->ce_exchange = all_ok == 1;
+            if (!op->ce_exchange && getenv("LS_DEBUG")) fprintf(stderr, "[ls_cuda] rank %d: IPC exchange unavailable (%s), using the NCCL all-to-all\n", rank, ls_last_error());
+        }
     }
 #undef TRY
     *out = reinterpret_cast<ls_handle>(op);
@@ -532,6 +618,17 @@ int ls_nccl_unique_id(void* out128) {
     if (r != ncclSuccess) { set_error("ncclGetUniqueId failed: %s", ncclGetErrorString(r)); return LS_ERR_NCCL; }
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     memcpy(out128, &id, sizeof(id));
+    return LS_OK;
+}
+
+int ls_op3d_info(ls_handle h, int* padding_factor, int* x_slot_chunks, int* exchange) {
+    LS_REQUIRE(h, LS_ERR_INVALID, "ls_op3d_info: null handle");
+    HandleBase* base = reinterpret_cast<HandleBase*>(h);
+    LS_REQUIRE(base->kind == KIND_OP3D, LS_ERR_INVALID, "ls_op3d_info: not a 3-D operator handle");
+    Op3D* op = dynamic_cast<Op3D*>(base);
+    if (padding_factor) *padding_factor = op ? op->nr : 4;
+    if (x_slot_chunks) *x_slot_chunks = op ? op->Cx : 1;
+    if (exchange) *exchange = (op && op->P > 1) ? (op->ce_exchange ? 2 : 1) : 0;
     return LS_OK;
 }
 

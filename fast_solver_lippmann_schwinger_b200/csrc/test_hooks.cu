@@ -84,3 +84,77 @@ extern "C" int ls_test_fft_lines(int64_t N, int64_t nlines, const ls_cdouble* in
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_W);
     return rc;
 }
+
+// ---- measured device peaks for the roofline denominators of bench.py ----------------------------------------------
+// FP64: 8 independent dependent-chains per thread of DFMA (or DADD) instructions, enough warps to fill every SM.
+namespace {
+template <bool FMA>
+__global__ void __launch_bounds__(256)
+k_fp64_peak(double* out, int iters, double b, double c) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        if (FMA) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        } else {
+            a0 = __dadd_rn(a0, c); a1 = __dadd_rn(a1, c); a2 = __dadd_rn(a2, c); a3 = __dadd_rn(a3, c);
+            a4 = __dadd_rn(a4, c); a5 = __dadd_rn(a5, c); a6 = __dadd_rn(a6, c); a7 = __dadd_rn(a7, c);
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) out[0] = s;      // keeps the chains alive
+}
+__global__ void __launch_bounds__(256)
+k_copy_peak(const double2* __restrict__ src, double2* __restrict__ dst, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+// dfma_tflops: 2 flops per DFMA lane;  dadd_tinst: 1e12 FP64 lane-instructions per second (DADD; DMUL issues alike);
+// copy_gbs: read + write bytes of a 1 GiB device-to-device copy kernel (the HBM roofline this library's kernels see)
+extern "C" int ls_test_device_peaks(double* dfma_tflops, double* dadd_tinst, double* copy_gbs) {
+    cudaEvent_t e0, e1;
+    LS_CUDA_TRY(cudaEventCreate(&e0));
+    LS_CUDA_TRY(cudaEventCreate(&e1));
+    double* d_out = nullptr;
+    LS_CUDA_TRY(cudaMalloc(&d_out, 64));
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int blocks = sms * 8, iters = 1 << 15;
+    float ms = 0.f, best[2] = {1e30f, 1e30f};
+    for (int which = 0; which < 2; ++which)
+        for (int rep = 0; rep < 4; ++rep) {
+            LS_CUDA_TRY(cudaEventRecord(e0));
+            if (which == 0) k_fp64_peak<true><<<blocks, 256>>>(d_out, iters, 1.0000001, 1e-9);
+            else k_fp64_peak<false><<<blocks, 256>>>(d_out, iters, 1.0000001, 1e-9);
+            LS_CUDA_TRY(cudaEventRecord(e1));
+            LS_CUDA_TRY(cudaEventSynchronize(e1));
+            LS_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best[which]) best[which] = ms;
+        }
+    const double lane_ops = (double)blocks * 256.0 * iters * 8.0;
+    if (dfma_tflops) *dfma_tflops = 2.0 * lane_ops / (best[0] * 1e-3) / 1e12;
+    if (dadd_tinst) *dadd_tinst = lane_ops / (best[1] * 1e-3) / 1e12;
+    cudaFree(d_out);
+    if (copy_gbs) {
+        const long n = 1L << 26;        // 1 GiB of double2
+        double2 *a = nullptr, *b = nullptr;
+        LS_CUDA_TRY(cudaMalloc(&a, n * sizeof(double2)));
+        LS_CUDA_TRY(cudaMalloc(&b, n * sizeof(double2)));
+        LS_CUDA_TRY(cudaMemset(a, 0, n * sizeof(double2)));
+        float bestc = 1e30f;
+        for (int rep = 0; rep < 6; ++rep) {
+            LS_CUDA_TRY(cudaEventRecord(e0));
+            k_copy_peak<<<sms * 16, 256>>>(a, b, n);
+            LS_CUDA_TRY(cudaEventRecord(e1));
+            LS_CUDA_TRY(cudaEventSynchronize(e1));
+            LS_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < bestc) bestc = ms;
+        }
+        *copy_gbs = 2.0 * n * sizeof(double2) / (bestc * 1e-3) / 1e9;
+        cudaFree(a); cudaFree(b);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return LS_OK;
+}

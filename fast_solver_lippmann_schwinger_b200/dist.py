@@ -93,6 +93,12 @@ class FastM3DSharded(_Handle):
     def eltype(self):
         return np.dtype(np.complex128)
 
+    def info(self):
+        """(padding factor, x-slot chunks, transpose route: 'single' / 'nccl' / 'copy-engine')."""
+        p, c, x = C.c_int(), C.c_int(), C.c_int()
+        check(lib().ls_op3d_info(self.handle, C.byref(p), C.byref(c), C.byref(x)))
+        return int(p.value), int(c.value), ("single", "nccl", "copy-engine")[x.value]
+
     _apply = FastM3D._apply
     __mul__ = FastM3D.__mul__
     __matmul__ = FastM3D.__mul__

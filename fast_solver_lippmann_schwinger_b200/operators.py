@@ -94,13 +94,26 @@ class FastM(_Handle):
     into a one-time device permutation).
     """
 
-    def __init__(self, GFFT, nu, ne, me, n, m, k, quadRule="trapezoidal", force_generic=False, pad4=False):
+    def __init__(self, GFFT, nu, ne, me, n, m, k, quadRule="trapezoidal", force_generic=False, pad4=False, L=None, Lp=None):
         super().__init__()
         self.ne, self.me, self.n, self.m = int(ne), int(me), int(n), int(m)
         self.omega = float(k)
         self.quadRule = quadRule
         if quadRule not in _lib.QUADRULES:
             raise ValueError("unknown quadRule %r" % (quadRule,))
+        if GFFT is None:
+            # Greengard_Vico spectrum Gtruncated2D(L, k, S) evaluated on the device (FastConvolution.jl:185-231)
+            if quadRule != "Greengard_Vico" or L is None or Lp is None:
+                raise ValueError("GFFT=None needs quadRule='Greengard_Vico' and the truncation parameters L, Lp")
+            if (self.ne, self.me) != (4 * self.n, 4 * self.m):
+                raise ValueError("DimensionMismatch: Greengard_Vico pads to (4n, 4m)")
+            nu = np.ascontiguousarray(np.asarray(nu, dtype=np.float64).reshape(-1))
+            if nu.shape[0] != self.n * self.m:
+                raise ValueError("DimensionMismatch: nu has %d entries, expected %d" % (nu.shape[0], self.n * self.m))
+            self.N = self.n * self.m
+            check(lib().ls_op2d_create_gv(C.byref(self._h), self.n, self.m, ptr(nu), self.omega, float(L), float(Lp),
+                                          (1 if force_generic else 0) | (2 if pad4 else 0)))
+            return
         GFFT = np.asarray(GFFT)
         if GFFT.shape != (self.ne, self.me):
             raise ValueError("DimensionMismatch: GFFT is %s, expected (%d, %d)" % (GFFT.shape, self.ne, self.me))

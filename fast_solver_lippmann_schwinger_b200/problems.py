@@ -17,6 +17,16 @@ def nu_gaussian_2d(X, Y):
     return 0.3 * np.exp(-40 * (X ** 2 + Y ** 2)) * (np.abs(X) < 0.48) * (np.abs(Y) < 0.48)
 
 
+def nu_plasma_2d(X, Y):
+    """tests/plasma_example.jl:53-68: the discontinuous plasma profile nu(x, y) = -nu2(3x, 3y) (config 3)."""
+    x, y = 3.0 * np.asarray(X, dtype=np.float64), 3.0 * np.asarray(Y, dtype=np.float64)
+    phi = 1 - (x - 0.05 * (1 - x ** 2)) ** 2 - 0.4987 * ((1 + 0.3 * x) ** 2) * y ** 2
+    bumps = ((0.45, 0.4, 0.0), (0.196, 0.54, -0.28), (0.51, -0.14, 0.70), (0.195, -0.5, -0.01), (0.63, 0.18, 0.8))
+    g = sum(a * np.exp(-((x - xi) ** 2 + (y - yi) ** 2) / 0.01) for a, xi, yi in bumps)
+    nu2 = (phi > 0.05) * (-1.5 * (phi - 0.05) - g * np.cos(0.9 * y))
+    return -nu2
+
+
 def gv_spectrum_2d(n, m, h, k):
     """GFFT of buildFastConvolution's Greengard_Vico branch (FastConvolution.jl:185-231;
     Gtruncated2D, Functions.jl:40-42), shape (4n, 4m), centred ordering."""
@@ -54,4 +64,19 @@ def nu_gaussian_3d_grid(n, a=1.0):
     x = -a / 2 + h * np.arange(n)
     g = np.exp(-40 * x ** 2) * (np.abs(x) < 0.48)
     nu = 0.3 * g[:, None, None] * g[None, :, None] * g[None, None, :]
+    return np.ascontiguousarray(nu.reshape(-1, order="F"))
+
+
+def nu_layered_3d_slab(n, p0, p1, a=1.0, values=(0.05, 0.10, 0.02, 0.08)):
+    """Config 5's synthetic contrast ("layered, piecewise constant in z"; the reference's
+    example3D_Polarized_traces.jl:45 itself ships the Gaussian bump): len(values) horizontal layers inside the box
+    |x|, |y|, |z| < 0.48 a, zero outside, on the n^3 grid x = -a/2:h:a/2-h.  Returns the z planes [p0, p1) flattened
+    (x fastest) - a rank's slab of the sharded operator."""
+    h = a / n
+    x = -a / 2 + h * np.arange(n)
+    box = (np.abs(x) < 0.48 * a).astype(np.float64)
+    z = x[p0:p1]
+    layer = np.clip(((z / a + 0.48) / 0.96 * len(values)).astype(int), 0, len(values) - 1)
+    vz = np.asarray(values, dtype=np.float64)[layer] * (np.abs(z) < 0.48 * a)
+    nu = box[:, None, None] * box[None, :, None] * vz[None, None, :]
     return np.ascontiguousarray(nu.reshape(-1, order="F"))

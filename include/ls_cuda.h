@@ -80,6 +80,11 @@ int ls_host_free_pinned(void* hptr);
 int ls_op2d_create(ls_handle* out, int64_t n, int64_t m, int64_t ne, int64_t me,
                    const double* nu, const ls_cdouble* gfft, double omega,
                    int quadrule, int flags);
+/* The same operator with the Greengard_Vico spectrum GFFT = Gtruncated2D(L, k, S) (Functions.jl:40-42) on the grid
+ * S = (2 pi/Lp) |(-2n:2n-1, -2m:2m-1)| of buildFastConvolution (FastConvolution.jl:185-231; there L = 1.5 (x[end]-x[1]+h),
+ * Lp = 4 (x[end]-x[1]+h)) evaluated on the device straight into the kernel layout: no host Bessel evaluation and no
+ * 16*ne*me-byte upload (4.3 GB at n = 4096).  omega = k.  Power-of-two fast path and the general-size path alike.   */
+int ls_op2d_create_gv(ls_handle* out, int64_t n, int64_t m, const double* nu, double omega, double L, double Lp, int flags);
 /* y = M*b (mode 0; `*` FastConvolution.jl:43-48, mul! :50-54) or FFTconvolution(M,b) (mode 1).
  * b and y hold n*m complex values and may alias.                                          */
 int ls_op2d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc);
@@ -99,14 +104,18 @@ int ls_op3d_create(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, 
                    int flags);
 /* Sharded 3-D operator, one process per GPU (P = 2, 4 or 8 ranks of one NVLink/NVSwitch box).
  * Rank r owns the z planes [r*l/P, (r+1)*l/P): nu_slab, and the b / y of ls_op3d_apply, are that
- * contiguous range of n*m*l/P values.  The padded FFT is slab-decomposed; its two transposes are
- * NCCL all-to-alls on the communicator created here from `nccl_unique_id` (128 bytes obtained
+ * contiguous range of n*m*l/P values.  The padded FFT is slab-decomposed; its two transposes push contiguous blocks
+ * into the peers' IPC-mapped exchange buffers with the copy engines over NVLink (LS_OP3D_XCHG=nccl: grouped
+ * ncclSend/ncclRecv instead), synchronised on the communicator created here from `nccl_unique_id` (128 bytes obtained
  * with ls_nccl_unique_id on rank 0 and broadcast by the host: torch.distributed / MPI /
  * Distributed.jl).  Collective: every rank must call create and each apply.                   */
 int ls_nccl_unique_id(void* out128);
 int ls_op3d_create_dist(ls_handle* out, int64_t n, int64_t m, int64_t l, const double* nu_slab,
                         double omega, double L, double Lp, int rank, int nranks,
                         const void* nccl_unique_id, int flags);
+/* how the handle evaluates: padding factor in use (2 compact / 4 literal), x-slot chunks of the pipelined transposes,
+ * transpose route (0: single GPU, 1: NCCL grouped send/recv, 2: copy-engine pushes into IPC-mapped peer buffers)      */
+int ls_op3d_info(ls_handle h, int* padding_factor, int* x_slot_chunks, int* exchange);
 /* mode 0: `*(M::FastM3D, b)` = b + omega^2 FFTconvolution(M, nu.*b)  (FastConvolution3D.jl:31-37)
  * mode 1: FFTconvolution(M, b)                                      (FastConvolution3D.jl:39-63) */
 int ls_op3d_apply(ls_handle h, const ls_cdouble* b, ls_cdouble* y, int mode, int memloc);
@@ -210,6 +219,10 @@ int ls_profile_read(ls_handle h, double* ms_per_phase, int64_t* launches_per_pha
  * the line-FFT engine; device-side unit test of fft_engine.cuh.                           */
 int ls_test_fft_lines(int64_t N, int64_t nlines, const ls_cdouble* in_host, ls_cdouble* out_host,
                       int inverse_roundtrip);
+
+/* measured device peaks used as roofline denominators by bench.py: FP64 FMA TFLOP/s, FP64 add/mul lane-instructions
+ * per second (in 1e12), and the read+write GB/s of a plain 1 GiB copy kernel                                     */
+int ls_test_device_peaks(double* dfma_tflops, double* dadd_tinst, double* copy_gbs);
 
 #ifdef __cplusplus
 }

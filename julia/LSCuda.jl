@@ -165,14 +165,42 @@ function cscmv!(alpha::ComplexF64, A::GPUSparseMatrixCSC, x::Vector{ComplexF64},
 end
 *(A::GPUSparseMatrixCSC, x::Vector{ComplexF64}) = cscmv!(1.0 + 0im, A, x, 0.0 + 0im, zeros(ComplexF64, A.m))
 
+"""
+`lu(Msp)` (preconditioner.jl:35) on the GPU: nested-dissection factorisation of the 9-point matrix Msp of the
+n x m grid.  `F \\ b` solves on host vectors; inside `gmres_gpu!` the solve never leaves the device.
+"""
+struct GPUMspFactorization
+    h::Handle
+    N::Int64
+end
+function GPUMspFactorization(Msp::SparseMatrixCSC{ComplexF64,Int64}, n::Integer, m::Integer)
+    size(Msp, 1) == size(Msp, 2) == n * m || throw(DimensionMismatch("Msp is $(size(Msp)), the grid has $(n*m) unknowns"))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ls_msp_factor, libls), Cint, (Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}),
+                out, n, m, Msp.colptr, Msp.rowval, Msp.nzval))
+    return GPUMspFactorization(Handle(out[]), n * m)
+end
+function \(F::GPUMspFactorization, b::Vector{ComplexF64})
+    x = similar(b)
+    check(ccall((:ls_msp_solve, libls), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint), F.h.ptr, b, x, LS_MEM_HOST))
+    return x
+end
+function msp_info(F::GPUMspFactorization)
+    fb = Ref{Int64}(0); dep = Ref{Cint}(0); sec = Ref{Float64}(0.0)
+    check(ccall((:ls_msp_info, libls), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Cint}, Ref{Float64}), F.h.ptr, fb, dep, sec))
+    return (factor_bytes=fb[], depth=dep[], factor_seconds=sec[])
+end
+
 struct GPUSparsifyingPreconditioner      # preconditioner.jl:27-58
     Msp::SparseMatrixCSC{ComplexF64,Int64}
     As::GPUSparseMatrixCSC
-    MspInv                                 # lu(Msp) (UMFPACK) stays on the host - out of the GPU path's scope
+    MspInv                                 # lu(Msp): UMFPACK on the host, or GPUMspFactorization (solverType = "GPU")
     solverType::String
 end
-GPUSparsifyingPreconditioner(Msp, As; solverType::String="UMFPACK") =
-    GPUSparsifyingPreconditioner(Msp, GPUSparseMatrixCSC(As), lu(Msp), solverType)
+"solverType = \"UMFPACK\" / \"MKLPARDISO\" as upstream (host LU, reached through the ls_solve_cb callback), or \"GPU\" with grid = (n, m)."
+GPUSparsifyingPreconditioner(Msp, As; solverType::String="UMFPACK", grid=nothing) =
+    GPUSparsifyingPreconditioner(Msp, GPUSparseMatrixCSC(As),
+                                 solverType == "GPU" ? GPUMspFactorization(Msp, grid[1], grid[2]) : lu(Msp), solverType)
 \(M::GPUSparsifyingPreconditioner, b::Array{ComplexF64,1}) = M.MspInv \ (M.As * b)                     # :132-145
 function ldiv!(M::GPUSparsifyingPreconditioner, b::AbstractArray{ComplexF64,1})                        # :147-166
     b[:] = M.MspInv \ (M.As * Vector(b))
@@ -183,8 +211,8 @@ end
     gmres_gpu!(x, A, b; Pl=nothing, abstol, reltol, restart, maxiter, log, initially_zero)
 
 Same keywords and history semantics as `IterativeSolvers.gmres!`; the Krylov basis, the modified
-Gram-Schmidt sweeps and the operator applies stay on the device, `Msp^-1` is reached through a
-host callback.
+Gram-Schmidt sweeps and the operator applies stay on the device; `Msp^-1` runs on the device too when the
+preconditioner was built with solverType = "GPU", else it is reached through a host callback.
 """
 function gmres_gpu!(x::Vector{ComplexF64}, A, b::Vector{ComplexF64}; Pl=nothing, abstol=0.0,
                     reltol=sqrt(eps(Float64)), restart=min(20, length(b)), maxiter=length(b), log=false,
@@ -196,6 +224,14 @@ function gmres_gpu!(x::Vector{ComplexF64}, A, b::Vector{ComplexF64}; Pl=nothing,
     check(ccall((:ls_krylov_set_orth, libls), Cint, (Ptr{Cvoid}, Cint), K.ptr, LS_ORTH[orth_meth]))
     hist = zeros(Float64, maxiter); niter = Ref{Int64}(0); conv = Ref{Cint}(0); mv = Ref{Int64}(0)
     cb = C_NULL; as = C_NULL
+    if Pl !== nothing && Pl.MspInv isa GPUMspFactorization      # Msp^-1 (As v) entirely on the device
+        check(ccall((:ls_gmres_msp, libls), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Int64,
+             Float64, Float64, Cint, Ptr{Float64}, Int64, Ref{Int64}, Ref{Cint}, Ref{Int64}, Cint),
+            K.ptr, A.h.ptr, Pl.As.h.ptr, Pl.MspInv.h.ptr, b, x, restart, maxiter,
+            reltol, abstol, initially_zero, hist, maxiter, niter, conv, mv, LS_MEM_HOST))
+        return log ? (x, (resnorm=hist[1:niter[]], iters=niter[], isconverged=conv[] != 0, mvps=mv[])) : x
+    end
     if Pl !== nothing
         solve = function (user::Ptr{Cvoid}, v::Ptr{ComplexF64}, n::Int64)::Cint
             w = unsafe_wrap(Array, v, n)
@@ -213,7 +249,7 @@ function gmres_gpu!(x::Vector{ComplexF64}, A, b::Vector{ComplexF64}; Pl=nothing,
     return log ? (x, (resnorm=hist[1:niter[]], iters=niter[], isconverged=conv[] != 0, mvps=mv[])) : x
 end
 
-export GPUFastM, GPUFastM3D, GPUFastM3DSharded, nccl_unique_id, GPUSparsifyingPreconditioner, GPUSparseMatrixCSC, fastconvolution, FFTconvolution,
+export GPUFastM, GPUFastM3D, GPUFastM3DSharded, nccl_unique_id, GPUSparsifyingPreconditioner, GPUSparseMatrixCSC, GPUMspFactorization, msp_info, fastconvolution, FFTconvolution,
        gmres_gpu!, cscmv!, set_device
 
 end # module

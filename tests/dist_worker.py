@@ -76,6 +76,16 @@ def main():
     assert np.linalg.norm(y4 - y_ref[a:b_]) / np.linalg.norm(y_ref[a:b_]) <= 1e-12
     assert np.linalg.norm((y4 - y)) / np.linalg.norm(y_ref[a:b_]) <= 1e-13
     M4.destroy()
+    # the default transposes run on the copy engines (pushes into IPC-mapped peer buffers); the NCCL all-to-all gives the same bits
+    assert M.info() == (2, 1, "copy-engine"), M.info()
+    os.environ["LS_OP3D_XCHG"] = "nccl"
+    uidn = lsd.broadcast_unique_id(rank)
+    Mn = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uidn)
+    del os.environ["LS_OP3D_XCHG"]
+    assert Mn.info()[2] == "nccl"
+    yn = Mn * np.ascontiguousarray(b[a:b_])
+    assert np.array_equal(yn, y)
+    Mn.destroy()
     # large slabs pipeline their transposes over x-slot chunks (on a second stream); forced here: same bits
     os.environ["LS_OP3D_CHUNKS"] = "4"
     uid1 = lsd.broadcast_unique_id(rank)

@@ -119,3 +119,29 @@ def test_compact_padding_equals_literal_4x(n, m):
     B2 = ls.FastM(G, nu, 4 * n, 4 * m, n, m, 1.3, quadRule="Greengard_Vico")
     Bo = O.FastM(G, nu, 4 * n, 4 * m, n, m, 1.3, quadRule="Greengard_Vico")
     assert _rel(B2 * b, O.fastconvolution(Bo, b)) <= TOL
+
+
+@pytest.mark.parametrize("n,m", [(64, 64), (256, 128), (100, 100)])
+def test_spectrum_generated_on_the_device(n, m):
+    """ls_op2d_create_gv: Gtruncated2D (Functions.jl:40-42) evaluated on the device (own J0 / J1 expansions, host Hankel
+    scalars) gives the same operator as the host-built GFFT, on the power-of-two and on the general-size path."""
+    from oracle import ls_oracle as O
+    import fast_solver_lippmann_schwinger_b200 as ls
+    h = 1.0 / n
+    x = -0.5 + h * np.arange(n)
+    y = -0.5 * m / n + h * np.arange(m)
+    k = 2 * np.pi / (10 * h)
+    Mo = O.buildFastConvolution(x, y, h, k, O.nu_gaussian_2d, quadRule="Greengard_Vico")
+    # L, Lp exactly as buildFastConvolution takes them (FastConvolution.jl:187-188)
+    Lp = 4.0 * (x[-1] - x[0] + h)
+    L = 1.5 * (x[-1] - x[0] + h)
+    Mg = ls.FastM(None, Mo.nu, 4 * n, 4 * m, n, m, k, quadRule="Greengard_Vico", L=L, Lp=Lp)
+    rng = np.random.default_rng(n + m)
+    b = rng.standard_normal(n * m) + 1j * rng.standard_normal(n * m)
+    assert _rel(Mg * b, O.fastconvolution(Mo, b)) < 1e-12
+    if n == m:
+        assert _rel(ls.FFTconvolution(Mg, b), O.FFTconvolution(Mo, b)) < 1e-12
+    Mh = ls.FastM(Mo.GFFT, Mo.nu, 4 * n, 4 * m, n, m, k, quadRule="Greengard_Vico")
+    assert _rel(Mg * b, Mh * b) < 1e-13
+    with pytest.raises(ValueError):
+        ls.FastM(None, Mo.nu, 4 * n, 4 * m, n, m, k, quadRule="Greengard_Vico")          # needs L, Lp

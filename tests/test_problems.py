@@ -24,3 +24,15 @@ def test_nu_gaussian_3d_grid():
     x = -0.5 + h * np.arange(n)
     X, Y, Z = O.grid3d(x, x, x)
     assert np.allclose(nu_gaussian_3d_grid(n), O.nu_gaussian_3d(X, Y, Z), rtol=1e-14, atol=1e-18)
+
+
+def test_nu_plasma_2d_matches_the_oracle():
+    """Config 3 input builder (tests/plasma_example.jl:53-68) against the oracle's restatement."""
+    from oracle import ls_oracle as O
+    from fast_solver_lippmann_schwinger_b200.problems import nu_plasma_2d
+    n = 96
+    x = -0.5 + np.arange(n) / n
+    X, Y = O.grid2d(x, x)
+    a, b = nu_plasma_2d(X, Y), O.nu_plasma_2d(X, Y)
+    assert np.abs(a - b).max() <= 1e-15 * np.abs(b).max()
+    assert (a == 0).sum() > 100 and np.unique(a).size > 100
