@@ -64,6 +64,22 @@ function GPUFastM(GFFT::Array{ComplexF64,2}, nu::Vector{Float64}, ne, me, n, m, 
 end
 "Move an existing reference operator to the GPU."
 GPUFastM(M) = GPUFastM(M.GFFT, M.nu, M.ne, M.me, M.n, M.m, M.omega; quadRule=M.quadRule)
+"""
+    GPUFastM(x, y, h, k, nu)
+
+GPU twin of `buildFastConvolution(x, y, h, k, nu, quadRule = "Greengard_Vico")` (FastConvolution.jl:185-231) that never
+builds GFFT on the host: the spectrum Gtruncated2D(L, k, S) is evaluated on the device (ls_op2d_create_gv).
+"""
+function GPUFastM(x::AbstractVector, y::AbstractVector, h::Real, k::Real, nu::Function)
+    (n, m) = length(x), length(y)
+    Lp = 4 * (abs(x[end] - x[1]) + h); L = 1.5 * (abs(x[end] - x[1]) + h)
+    X = repeat(x, 1, m)[:]; Y = repeat(y', n, 1)[:]
+    nuv = Vector{Float64}(nu(X, Y))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ls_op2d_create_gv, libls), Cint, (Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{Float64}, Float64, Float64, Float64, Cint),
+                out, n, m, nuv, Float64(k), Float64(L), Float64(Lp), 0))
+    return GPUFastM(Handle(out[]), nuv, 4n, 4m, n, m, Float64(k), "Greengard_Vico")
+end
 
 size(M::GPUFastM, dim) = length(M.nu)                       # FastConvolution.jl:31-33
 size(M::GPUFastM) = (size(M.nu), size(M.nu))                # :35-37 (tuple of tuples, kept)
@@ -129,6 +145,13 @@ function GPUFastM3DSharded(nu_slab::Vector{Float64}, n, m, l, k, L, Lp, rank::In
                 (Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Ptr{Float64}, Float64, Float64, Float64, Cint, Cint, Ptr{UInt8}, Cint),
                 out, n, m, l, nu_slab, Float64(k), Float64(L), Float64(Lp), rank, nranks, id, pad4 ? LS_FLAG_PAD4 : 0))
     return GPUFastM3D(Handle(out[]), nu_slab, 4n, 4m, 4l, n, m, l, Float64(k), "Greengard_Vico")
+end
+
+"(padding factor in use, x-slot chunks, transpose route: 0 single GPU / 1 NCCL send-recv / 2 copy-engine pushes)"
+function op3d_info(M::GPUFastM3D)
+    p = Ref{Cint}(0); c = Ref{Cint}(0); x = Ref{Cint}(0)
+    check(ccall((:ls_op3d_info, libls), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cint}, Ref{Cint}), M.h.ptr, p, c, x))
+    return (padding=p[], chunks=c[], exchange=x[])
 end
 
 """
