@@ -479,7 +479,6 @@ def bench_gmres_precond(args, ls, peak):
     """Config 3 (tests/plasma_example.jl:20-68,160-176 at BASELINE's grid): discontinuous plasma contrast, Greengard_Vico
     operator, sparsifying preconditioner built from GPU operator applies (buildSparseAConv / buildSparseAGConv),
     As*b and Msp^-1 on the GPU, GMRES(20) to reltol 1e-8.  Columns as SURVEY.md H1 asks: GPU loop, Msp solve, PCIe."""
-    import scipy.sparse as sp
     from fast_solver_lippmann_schwinger_b200 import sparsifier as S
     from fast_solver_lippmann_schwinger_b200.problems import nu_plasma_2d
     n = args.precond_n
@@ -494,10 +493,7 @@ def bench_gmres_precond(args, ls, peak):
     M = ls.FastM(None, nu, 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico", L=1.5 * n * h, Lp=4.0 * n * h)
     t_op = time.perf_counter() - t0
     t0 = time.perf_counter()
-    cache = S.entriesSparseAConv(k, X, Y, M, n, n, strict=False)
-    As = S.buildSparseAConv(k, X, Y, M, n, n, strict=False, _cache=cache)
-    AG = S.buildSparseAGConv(k, X, Y, M, n, n, strict=False, _cache=cache)
-    Msp = (As + k ** 2 * (AG @ sp.diags(nu))).tocsc()
+    As, Msp = S.sparsifying_matrices_2d(k, X, Y, M, n, n, nu, strict=False)    # 49 applies, rows and Gram matrices on the device
     t_sp = time.perf_counter() - t0
     t0 = time.perf_counter()
     Pl = ls.SparsifyingPreconditioner(Msp, As, solverType="GPU", grid=(n, n))

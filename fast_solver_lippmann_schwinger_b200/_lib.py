@@ -108,6 +108,9 @@ def lib():
         "ls_gmres_msp": (ci, [vp, vp, vp, vp, vp, vp, ci, i64, dbl, dbl, ci, vp, i64,
                               C.POINTER(i64), C.POINTER(ci), C.POINTER(i64), ci]),
         "ls_krylov_last_precond_host_seconds": (ci, [vp, C.POINTER(dbl)]),
+        "ls_sample_rows": (ci, [vp, vp, vp, ci, vp, i64]),
+        "ls_gram": (ci, [vp, vp, i64, ci, vp]),
+        "ls_gather_rows": (ci, [vp, vp, i64, ci, vp, ci, vp]),
         "ls_destroy": (ci, [vp]),
         "ls_sync": (ci, [vp]),
         "ls_timer_start": (ci, [vp]),

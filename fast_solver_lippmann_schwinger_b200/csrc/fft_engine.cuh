@@ -183,10 +183,20 @@ template <int N> struct LayA {
         return base + (l ^ ((l >> sh) & 7));
     }
 };
-// B: eight lines interleaved point by point (lane%8 = line) - conflict free by construction
+// B: LB adjacent lines interleaved point by point (lane % LB = line).  LB = 8: a quarter warp reads one point of eight
+// lines = 128 contiguous bytes, conflict free by construction.  LB = 4 (512-point lines: half the shared memory and
+// threads per CTA, so two CTAs fit an SM): a quarter warp spans two points t, t+1 (t even) of four lines, i.e. two
+// 64-byte pieces that must fall into different halves of the 32 banks - true when the two logical addresses differ in
+// parity, which the XOR with bit log2(RLAST) arranges for the last stage (addresses 8t + a and 8(t+1) + a there).
+template <int N> struct LinesB { static constexpr int value = (N == 512) ? 4 : 8; };
 template <int N> struct LayB {
+    static constexpr int LB = LinesB<N>::value;
     int lam;
-    __device__ __forceinline__ int phys(int l) const { return l * 8 + lam; }
+    __device__ __forceinline__ int phys(int l) const {
+        if (LB == 8) return l * 8 + lam;
+        constexpr int sh = ilog2(Stage<N, 0>::RLAST);
+        return (l ^ ((l >> sh) & 1)) * LB + lam;
+    }
 };
 
 template <int N, int I, class Lay>

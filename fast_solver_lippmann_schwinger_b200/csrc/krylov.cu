@@ -753,6 +753,86 @@ int ls_gmres_msp(ls_handle kh, ls_handle op_h, ls_handle as_h, ls_handle msp_h,
                         niter, converged, mv_products, memloc);
 }
 
+// ---- sparsifier sampling on the device --------------------------------------------------------
+// sampleGConv (FastConvolution.jl:278-306) / sampleG3D (FastConvolution3D.jl:136-160): row i of the discrete Green's
+// operator = FFTconvolution(fastconv, e_{indS[i]}).  The rows stay on the device (column i of V), so the far-field
+// Gram matrix of entriesSparseAConv (SparsifyingMatrix2D.jl:104-201: svd of the s x N block) is a handful of fused
+// multi-dot sweeps and only s^2 numbers reach the host.
+namespace {
+__global__ void k_set_unit(cd* e, long idx_prev, long idx) {
+    if (idx_prev >= 0) e[idx_prev] = make_double2(0.0, 0.0);
+    e[idx] = make_double2(1.0, 0.0);
+}
+__global__ void k_gather_rows(const cd* __restrict__ V, long ldv, int s, const long* __restrict__ idx, int nidx, cd* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < s * nidx) out[e] = V[idx[e % nidx] + (long)(e / nidx) * ldv];
+}
+}  // namespace
+
+int ls_sample_rows(ls_handle kh, ls_handle op_h, const int64_t* indS, int s, ls_cdouble* V_dev, int64_t ldv) {
+    KRYLOV_HANDLE(K, kh, "ls_sample_rows");
+    LS_REQUIRE(op_h && indS && V_dev && s > 0, LS_ERR_INVALID, "ls_sample_rows: bad argument");
+    HandleBase* op = reinterpret_cast<HandleBase*>(op_h);
+    LS_REQUIRE(op->op_size() == K->n && ldv >= K->n, LS_ERR_INVALID, "ls_sample_rows: operator size %ld, workspace %ld, ldv %ld",
+               (long)op->op_size(), (long)K->n, (long)ldv);
+    LS_REQUIRE(op->nccl_comm() == nullptr, LS_ERR_UNSUPPORTED, "ls_sample_rows: single-GPU operators only");
+    const size_t vb = (size_t)K->n * sizeof(cd);
+    if (!K->d_ax) {
+        int rc;
+        if ((rc = K->dmalloc((void**)&K->d_ax, vb))) return rc;
+        if ((rc = K->dmalloc((void**)&K->d_b, vb))) return rc;
+        if ((rc = K->dmalloc((void**)&K->d_x, vb))) return rc;
+    }
+    cudaStream_t st = op->stream;
+    LS_CUDA_TRY(cudaMemsetAsync(K->d_b, 0, vb, st));
+    long prev = -1;
+    for (int i = 0; i < s; ++i) {
+        LS_REQUIRE(indS[i] >= 1 && indS[i] <= K->n, LS_ERR_INVALID, "ls_sample_rows: stencil index %ld outside the grid", (long)indS[i]);
+        k_set_unit<<<1, 1, 0, st>>>(K->d_b, prev, indS[i] - 1);
+        prev = indS[i] - 1;
+        int rc = op->apply_dev(K->d_b, reinterpret_cast<cd*>(V_dev) + (long)i * ldv, LS_APPLY_FFTCONVOLUTION);
+        if (rc) return rc;
+        K->launches++;
+    }
+    LS_CUDA_TRY(cudaStreamSynchronize(st));
+    return LS_OK;
+}
+
+// gram[i + s*j] = sum_c conj(V[c, i]) V[c, j]   (host, column-major s x s); V: device, N x s, leading dimension ldv
+int ls_gram(ls_handle kh, const ls_cdouble* V_dev, int64_t ldv, int s, ls_cdouble* gram_host) {
+    KRYLOV_HANDLE(K, kh, "ls_gram");
+    LS_REQUIRE(V_dev && gram_host && s > 0 && s <= 64 && ldv >= K->n, LS_ERR_INVALID, "ls_gram: bad argument (s in [1, 64], ldv >= n)");
+    const cd* V = reinterpret_cast<const cd*>(V_dev);
+    for (int j = 0; j < s; ++j) {
+        int rc = K->multi_dot(V, ldv, s, V + (long)j * ldv, K->d_scal, K->stream);
+        if (rc) return rc;
+        LS_CUDA_TRY(cudaMemcpyAsync(K->h_scal, K->d_scal, 2 * (size_t)s * sizeof(double), cudaMemcpyDeviceToHost, K->stream));
+        LS_CUDA_TRY(cudaStreamSynchronize(K->stream));
+        memcpy(gram_host + (size_t)j * s, K->h_scal, 2 * (size_t)s * sizeof(double));
+    }
+    return LS_OK;
+}
+
+// out[j + nidx*i] = V[idx[j] - 1, i]  (idx 1-based, host; out host): the s x s near-field blocks of the sampled rows
+int ls_gather_rows(ls_handle kh, const ls_cdouble* V_dev, int64_t ldv, int s, const int64_t* idx, int nidx, ls_cdouble* out_host) {
+    KRYLOV_HANDLE(K, kh, "ls_gather_rows");
+    LS_REQUIRE(V_dev && idx && out_host && s > 0 && nidx > 0, LS_ERR_INVALID, "ls_gather_rows: bad argument");
+    std::vector<long> h((size_t)nidx);
+    for (int j = 0; j < nidx; ++j) {
+        LS_REQUIRE(idx[j] >= 1 && idx[j] <= K->n, LS_ERR_INVALID, "ls_gather_rows: index %ld outside the grid", (long)idx[j]);
+        h[(size_t)j] = idx[j] - 1;
+    }
+    long* d_idx = nullptr; cd* d_out = nullptr;
+    int rc;
+    if ((rc = K->dupload((void**)&d_idx, h.data(), h.size() * sizeof(long)))) return rc;
+    if ((rc = K->dmalloc((void**)&d_out, (size_t)s * nidx * sizeof(cd)))) return rc;
+    k_gather_rows<<<(s * nidx + 127) / 128, 128, 0, K->stream>>>(reinterpret_cast<const cd*>(V_dev), ldv, s, d_idx, nidx, d_out);
+    LS_CUDA_TRY(cudaMemcpyAsync(out_host, d_out, (size_t)s * nidx * sizeof(cd), cudaMemcpyDeviceToHost, K->stream));
+    LS_CUDA_TRY(cudaStreamSynchronize(K->stream));
+    K->dfree(d_idx); K->dfree(d_out);
+    return LS_OK;
+}
+
 int ls_krylov_last_precond_host_seconds(ls_handle kh, double* seconds) {
     KRYLOV_HANDLE(K, kh, "ls_krylov_last_precond_host_seconds");
     LS_REQUIRE(seconds, LS_ERR_INVALID, "ls_krylov_last_precond_host_seconds: null pointer");

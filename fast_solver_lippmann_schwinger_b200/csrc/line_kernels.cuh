@@ -28,9 +28,16 @@ template <int N> struct GeoA {
 template <int N> struct GeoB {
     static constexpr int E = Cfg<N>::E;
     static constexpr int T = N / E;
-    static constexpr int GPC = (T >= 16) ? 1 : 16 / T;     // groups of 8 lines per CTA
-    static constexpr int LPC = 8 * GPC;
-    static constexpr int THREADS = 8 * T * GPC;
+    static constexpr int LB = LinesB<N>::value;             // lines interleaved across lanes (8; 4 for 512-point lines)
+    static constexpr int GPC = (LB * T >= 128) ? 1 : 128 / (LB * T);     // groups of LB lines per CTA
+    static constexpr int LPC = LB * GPC;
+    static constexpr int THREADS = LB * T * GPC;
+};
+// resident CTAs per SM asked of ptxas: 128-thread CTAs 3 (168 registers); the 256-thread CTAs of the 4-line mode-B
+// geometry 2 (128 registers: E = 8 points per thread there); everything else 1
+template <int N, bool MODE_B> struct MinB {
+    static constexpr int TH = MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
+    static constexpr int value = (TH <= 128) ? 3 : ((MODE_B && GeoB<N>::LB == 4 && TH == 256) ? 2 : 1);
 };
 
 // thread -> (line within CTA, thread within line, smem layout)
@@ -53,12 +60,13 @@ template <int N> struct Map<N, true> {
     int line, t;
     Lay lay;
     __device__ __forceinline__ Map() {
-        int grp = threadIdx.x / (8 * G::T);
-        int w = threadIdx.x % (8 * G::T);
-        lay.lam = w & 7;
-        t = w >> 3;
-        line = grp * 8 + lay.lam;
-        smoff = grp * 8 * N;
+        constexpr int LB = G::LB;
+        int grp = threadIdx.x / (LB * G::T);
+        int w = threadIdx.x % (LB * G::T);
+        lay.lam = w % LB;
+        t = w / LB;
+        line = grp * LB + lay.lam;
+        smoff = grp * LB * N;
     }
     int smoff;
     __device__ __forceinline__ int lay_lam() const { return lay.lam; }
@@ -108,8 +116,7 @@ template <int N, bool MODE_B> struct Smem {
 // in  : line L point j at in[L*in_ls + j*in_es], optionally scaled by the real nu (same addressing)
 // out : line L slot  s at out[L*out_ls + s*out_es], s = r*N + slot
 template <int N, bool MODE_B>
-__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS,
-                                  ((MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS) <= 128) ? 3 : 1)   // 128-thread CTAs: 168 regs, 3 CTAs/SM
+__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MinB<N, MODE_B>::value)
 k_fwd_pruned(const cd* __restrict__ in, const double* __restrict__ nu, cd* __restrict__ out,
              const cd* __restrict__ TAB, const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
@@ -177,7 +184,8 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     typedef Map<N, MODE_B> M;
     constexpr int E = Cfg<N>::E, T = N / E, LPC = M::G::LPC;
     constexpr int AR = E - ASM, TH = MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
-    constexpr int UNIT = MODE_B ? 8 * N : N;          // points per spectrum chunk
+    constexpr int LBK = MODE_B ? GeoB<N>::LB : 1;     // lines interleaved in a spectrum chunk
+    constexpr int UNIT = LBK * N;                     // points per spectrum chunk
     constexpr int UPC = LPC * N / UNIT;               // chunks per CTA and r
     extern __shared__ __align__(128) cd sm[];
     M mp;
@@ -191,7 +199,7 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     const long L = Lcta + mp.line;
     const int t = mp.t;
     const int nr = la.nr, rstep = 4 / la.nr;
-    const cd* gsrc = G + (MODE_B ? (Lcta >> 3) : Lcta) * (long)nr * UNIT;   // chunk (unit u, rr) at gsrc + (u*nr + rr)*UNIT
+    const cd* gsrc = G + (Lcta / LBK) * (long)nr * UNIT;   // chunk (unit u, rr) at gsrc + (u*nr + rr)*UNIT
 
     auto issue_g = [&](int rr) {
         mbar_expect_tx(bar, (unsigned)(UPC * UNIT * sizeof(cd)));
@@ -214,9 +222,9 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
     // direct-load variant: pull spectrum chunk r into L2 one r ahead (one request per 128-byte line)
     auto prefetch_g = [&](int rr) {
         if (!GSM && rr < nr) {
-            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * nr + rr) * UNIT + mp.lay_lam()
+            const cd* g = MODE_B ? gsrc + ((long)(mp.line / LBK) * nr + rr) * UNIT + mp.lay_lam()
                                  : gsrc + ((long)mp.line * nr + rr) * UNIT;
-            constexpr int gs = MODE_B ? 8 : 1;
+            constexpr int gs = LBK;
             if (MODE_B ? (mp.lay_lam() == 0) : ((t & 7) == 0)) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) prefetch_l2(&g[(t + T * e) * gs]);
@@ -237,18 +245,18 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
         if (!GSM && MINB >= 3) {
             // three CTAs per SM: registers are the scarce resource, the other CTAs hide the load latency
             fft_fwd<N>(v, t, r, ex, mp.lay, tw);
-            const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * nr + rr) * UNIT + mp.lay_lam()
+            const cd* g = MODE_B ? gsrc + ((long)(mp.line / LBK) * nr + rr) * UNIT + mp.lay_lam()
                                  : gsrc + ((long)mp.line * nr + rr) * UNIT;
-            constexpr int gs = MODE_B ? 8 : 1;
+            constexpr int gs = LBK;
 #pragma unroll
             for (int e = 0; e < E; ++e) v[e] = cmul(v[e], __ldg(&g[(t + T * e) * gs]));
         } else if (!GSM) {
             // spectrum values are requested before the last butterfly stage and consumed after it
             cd gv[E];
             fft_fwd<N>(v, t, r, ex, mp.lay, tw, [&]() {
-                const cd* g = MODE_B ? gsrc + ((long)(mp.line >> 3) * nr + rr) * UNIT + mp.lay_lam()
+                const cd* g = MODE_B ? gsrc + ((long)(mp.line / LBK) * nr + rr) * UNIT + mp.lay_lam()
                                      : gsrc + ((long)mp.line * nr + rr) * UNIT;
-                constexpr int gs = MODE_B ? 8 : 1;
+                constexpr int gs = LBK;
 #pragma unroll
                 for (int e = 0; e < E; ++e) gv[e] = __ldg(&g[(t + T * e) * gs]);
             });
@@ -260,7 +268,7 @@ k_mid_fused(const cd* in, cd* out, const cd* __restrict__ G, const cd* __restric
         if (MODE_B) {
             const cd* g = gb + sm_group_off(mp);
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], g[(t + T * e) * 8 + mp.lay_lam()]);
+            for (int e = 0; e < E; ++e) v[e] = cmul(v[e], g[(t + T * e) * LBK + mp.lay_lam()]);
         } else {
             const cd* g = gb + goff;
 #pragma unroll
@@ -384,8 +392,7 @@ template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // cp.async while the current block is transformed (each thread stages exactly the elements it consumes: no
 // extra barrier), which takes two of the kernel's three exposed DRAM latencies off the critical path.
 template <int N, bool MODE_B, int PF = 0>
-__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS,
-                                  ((MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS) <= 128) ? 3 : 1)
+__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MinB<N, MODE_B>::value)
 k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __restrict__ TAB, double scale,
              const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;
@@ -493,8 +500,9 @@ inline cudaError_t launch_mid(cudaStream_t s, long nlines, const cd* in, cd* out
     constexpr int smem = GSM ? Smem<N, B>::mid_bytes : Smem<N, B>::mid_bytes_direct;
     constexpr int LPC = Smem<N, B>::LPC, TH = B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
     static unsigned long long optin = 0;
-    { cudaError_t e = smem_optin(k_mid_fused<N, B, GSM, 1>, smem, optin); if (e != cudaSuccess) return e; }
-    k_mid_fused<N, B, GSM, 1><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, out, G, TAB, la, 0);
+    constexpr int MB = (B && GeoB<N>::LB == 4) ? 2 : 1;      // 4-line geometry: two CTAs per SM (128 registers)
+    { cudaError_t e = smem_optin(k_mid_fused<N, B, GSM, MB>, smem, optin); if (e != cudaSuccess) return e; }
+    k_mid_fused<N, B, GSM, MB><<<(unsigned)(nlines / LPC), TH, smem, s>>>(in, out, G, TAB, la, 0);
     return cudaPeekAtLastError();
 }
 

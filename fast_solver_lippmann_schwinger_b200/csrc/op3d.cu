@@ -57,6 +57,14 @@ struct Op3D : HandleBase {
     bool ce_exchange = false;
     std::vector<cd*> peerA1, peerA1T;  // rank q's d_A1 / d_A1T mapped into this process (own entries: the local pointers)
     double* d_bar = nullptr;
+    // Completion signalling without a collective (default, LS_OP3D_SYNC=barrier keeps the all-reduce): after its pushes
+    // a rank stores the exchange's sequence number into flags[dir][rank] of every peer (one small kernel, system-scope
+    // stores over NVLink); the receiver's wait kernel spins until all P entries of flags[dir] have reached it.
+    bool flag_sync = true;
+    unsigned* d_flags = nullptr;             // [2][P] on this rank
+    std::vector<unsigned*> peerFlags;        // rank q's d_flags mapped here
+    unsigned** d_peerFlags = nullptr;        // the same table on the device
+    unsigned seq[2] = {0, 0};                // exchanges issued so far per direction
     cudaEvent_t evP1 = nullptr, evDone = nullptr;
     std::vector<cudaEvent_t> evIn, evOut;
     int64_t op_size() const override { return n * m * lloc; }
@@ -71,6 +79,7 @@ struct Op3D : HandleBase {
             if (q == rank) continue;
             if (peerA1[q]) cudaIpcCloseMemHandle(peerA1[q]);
             if (peerA1T[q]) cudaIpcCloseMemHandle(peerA1T[q]);
+            if (q < (int)peerFlags.size() && peerFlags[q]) cudaIpcCloseMemHandle(peerFlags[q]);
         }
         if (comm) ncclCommDestroy(comm);
         for (auto ev : evIn) cudaEventDestroy(ev);
@@ -81,7 +90,10 @@ struct Op3D : HandleBase {
     }
 };
 
+inline int lines_b(long N) { return N == 512 ? 4 : 8; }      // LinesB<N> of the mode-B kernels (fft_engine.cuh)
+
 struct GenParams {
+    int lb = 8;         // x-adjacent z lines interleaved per spectrum unit
     long n, m, l, ne, me, le;
     long nel, sx0;      // x-slot slab of this rank
     double dk;          // 2 pi / Lp
@@ -100,12 +112,12 @@ __global__ void k_fill_g3d(const cd* __restrict__ gin, cd* __restrict__ gout, co
                            const int* __restrict__ fy, const int* __restrict__ fz, GenParams p) {
     const long total = p.nel * p.me * p.le;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const long lam = idx & 7;
-        long q = idx >> 3;
+        const long lam = idx % p.lb;
+        long q = idx / p.lb;
         const long sz = q % p.l; q /= p.l;
         const long rz = q & 3;
         const long unit = q >> 2;
-        const long Lidx = unit * 8 + lam;
+        const long Lidx = unit * p.lb + lam;
         const long sx = p.sx0 + Lidx % p.nel, sy = Lidx / p.nel;
         const long kx = 4L * fx[sx % p.n] + sx / p.n;
         const long ky = 4L * fy[sy % p.m] + sy / p.m;
@@ -152,12 +164,38 @@ int all_to_all(Op3D* op, const cd* send, cd* recv, long blk_elems, cudaStream_t 
 // (offset `off` = chunk base in both); step s pushes to rank (rank + s) % P, so every rank receives from exactly one
 // source per step.  The closing all-reduce is the completion barrier: a rank leaves it only after every rank has
 // entered it, i.e. after every push (stream-ordered before the sender's all-reduce) has completed.
-int exchange_ce(Op3D* op, const cd* send, const std::vector<cd*>& peer, long off, long blk_elems, cudaStream_t on) {
+__global__ void k_xchg_signal(unsigned* const* peer_flags, int P, int slot, unsigned seq) {
+    const int q = threadIdx.x;
+    if (q < P) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned*>(peer_flags[q] + slot) = seq;
+    }
+}
+__global__ void k_xchg_wait(const unsigned* flags, int P, unsigned seq) {
+    const int q = threadIdx.x;
+    if (q < P) {
+        const volatile unsigned* f = flags + q;
+        const long long t0 = clock64();
+        while ((int)(*f - seq) < 0) {
+            if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a peer died - fail instead of hanging the GPU
+        }
+    }
+    __threadfence_system();
+}
+
+int exchange_ce(Op3D* op, const cd* send, const std::vector<cd*>& peer, long off, long blk_elems, cudaStream_t on, int dir) {
     const size_t bytes = (size_t)blk_elems * sizeof(cd);
     for (int st = 0; st < op->P; ++st) {
         const int q = (op->rank + st) % op->P;
         LS_CUDA_TRY(cudaMemcpyAsync(peer[q] + off + (long)op->rank * blk_elems, send + off + (long)q * blk_elems, bytes,
                                     cudaMemcpyDeviceToDevice, on));
+    }
+    if (op->flag_sync) {
+        const unsigned sq = ++op->seq[dir];
+        k_xchg_signal<<<1, 32, 0, on>>>(op->d_peerFlags, op->P, dir * op->P + op->rank, sq);
+        k_xchg_wait<<<1, 32, 0, on>>>(op->d_flags + dir * op->P, op->P, sq);
+        LS_CUDA_TRY(cudaPeekAtLastError());
+        return LS_OK;
     }
     ncclResult_t r = ncclAllReduce(op->d_bar, op->d_bar, 1, ncclDouble, ncclSum, op->comm, on);
     if (r != ncclSuccess) { set_error("exchange barrier failed: %s", ncclGetErrorString(r)); return LS_ERR_NCCL; }
@@ -167,11 +205,18 @@ int exchange_ce(Op3D* op, const cd* send, const std::vector<cd*>& peer, long off
 // maps the peers' exchange buffers into this process (all ranks of one box; handles travel by ncclAllGather)
 int setup_ce_exchange(Op3D* op) {
     const int P = op->P;
-    struct Pair { cudaIpcMemHandle_t a1, a1t; };
-    static_assert(sizeof(Pair) == 128, "two 64-byte IPC handles");
+    struct Pair { cudaIpcMemHandle_t a1, a1t, fl; };
+    static_assert(sizeof(Pair) == 192, "three 64-byte IPC handles");
     Pair mine;
+    {
+        // an allocation of its own (2 MiB: never packed with other small buffers), since the IPC handle maps whole allocations
+        int rc0 = op->dmalloc((void**)&op->d_flags, (size_t)2 << 20);
+        if (rc0) return rc0;
+        LS_CUDA_TRY(cudaMemset(op->d_flags, 0, (size_t)2 << 20));
+    }
     LS_CUDA_TRY(cudaIpcGetMemHandle(&mine.a1, op->d_A1));
     LS_CUDA_TRY(cudaIpcGetMemHandle(&mine.a1t, op->d_A1T));
+    LS_CUDA_TRY(cudaIpcGetMemHandle(&mine.fl, op->d_flags));
     char *d_send = nullptr, *d_recv = nullptr;
     int rc;
     if ((rc = op->dmalloc((void**)&d_send, sizeof(Pair)))) return rc;
@@ -189,14 +234,20 @@ int setup_ce_exchange(Op3D* op) {
     op->peerA1T.assign((size_t)P, nullptr);
     op->peerA1[op->rank] = op->d_A1;
     op->peerA1T[op->rank] = op->d_A1T;
+    op->peerFlags.assign((size_t)P, nullptr);
+    op->peerFlags[op->rank] = op->d_flags;
     for (int q = 0; q < P; ++q) {
         if (q == op->rank) continue;
-        void *p1 = nullptr, *p2 = nullptr;
+        void *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
         LS_CUDA_TRY(cudaIpcOpenMemHandle(&p1, all[q].a1, cudaIpcMemLazyEnablePeerAccess));
         op->peerA1[q] = (cd*)p1;
         LS_CUDA_TRY(cudaIpcOpenMemHandle(&p2, all[q].a1t, cudaIpcMemLazyEnablePeerAccess));
         op->peerA1T[q] = (cd*)p2;
+        LS_CUDA_TRY(cudaIpcOpenMemHandle(&p3, all[q].fl, cudaIpcMemLazyEnablePeerAccess));
+        op->peerFlags[q] = (unsigned*)p3;
     }
+    if ((rc = op->dupload((void**)&op->d_peerFlags, op->peerFlags.data(), (size_t)P * sizeof(unsigned*)))) return rc;
+    { const char* sv = getenv("LS_OP3D_SYNC"); op->flag_sync = !(sv && strcmp(sv, "barrier") == 0); }
     op->ce_exchange = true;
     return LS_OK;
 }
@@ -228,7 +279,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
         LS_CUDA_TRY(cudaStreamWaitEvent(sc, op->evP1, 0));
         for (int c = 0; c < Cx; ++c) {
             op->phase_begin(5, sc);
-            int rc = op->ce_exchange ? exchange_ce(op, op->d_A1, op->peerA1T, c * cstride, blk, sc)
+            int rc = op->ce_exchange ? exchange_ce(op, op->d_A1, op->peerA1T, c * cstride, blk, sc, 0)
                                      : all_to_all(op, op->d_A1 + c * cstride, op->d_A1T + c * cstride, blk, sc);
             op->phase_end(sc);
             if (rc) return rc;
@@ -286,7 +337,7 @@ int apply_device3(Op3D* op, const cd* b, cd* y, int mode) {
             LS_CUDA_TRY(cudaEventRecord(op->evOut[c], s));
             LS_CUDA_TRY(cudaStreamWaitEvent(sc, op->evOut[c], 0));
             op->phase_begin(6, sc);
-            int rc = op->ce_exchange ? exchange_ce(op, op->d_A1T, op->peerA1, c * cstride, blk, sc)
+            int rc = op->ce_exchange ? exchange_ce(op, op->d_A1T, op->peerA1, c * cstride, blk, sc, 1)
                                      : all_to_all(op, op->d_A1T + c * cstride, op->d_A1 + c * cstride, blk, sc);
             op->phase_end(sc);
             if (rc) return rc;
@@ -358,8 +409,10 @@ int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_
     if ((rc = op->dmalloc((void**)&T2, slab4 * sizeof(cd)))) return rc;
     if ((rc = op->dmalloc((void**)&g4c, (size_t)nelc * (4 * m) * (4 * l) * sizeof(cd)))) return rc;
     if ((rc = op->dmalloc((void**)&t1c, (size_t)nelc * (4 * m) * (2 * l) * sizeof(cd)))) return rc;
+    const long LBl = lines_b(l);             // lines per unit of the final (2x) spectrum = what the fused z pass reads
     for (int c = 0; c < C; ++c) {
         p.nel = nelc; p.sx0 = (long)rank * nel4 + c * nelc;
+        p.lb = 8;                            // set-up buffer: units of 8 lines, read below through explicit strides
         k_fill_g3d<<<148 * 16, 256, 0, s>>>(d_gin, g4c, d_fx, d_fy, d_fz, p);
         for (int cb = 0; cb <= 3; cb += 3) {     // (1) inverse z on the chunk: t1c[L + nelc*4m*jz2], L = sxl + nelc*sy4
             LineAddr la{8, 1, 32 * l, 8, 1, 8, nelc * 4 * m};
@@ -434,8 +487,8 @@ int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_
         Z = Y;
         G2 = X;
     }
-    {   // (6) forward z, lines L = sxl2 + nel2*sy2: Z[L + nel2*2m*jz2] -> G2[((L/8)*2 + rz)*8l + sz*8 + L%8]
-        LineAddr la{8, 1, 8, nel2 * 2 * m, 1, 16 * l, 8};
+    {   // (6) forward z, lines L = sxl2 + nel2*sy2: Z[L + nel2*2m*jz2] -> G2[((L/LB)*2 + rz)*LB*l + sz*LB + L%LB]
+        LineAddr la{LBl, 1, LBl, nel2 * 2 * m, 1, 2 * LBl * l, LBl};
         la.nr = 2; la.full2 = 1;
 #define Z2(N) launch_fwd<N, true>(s, nel2 * 2 * m, Z, nullptr, G2, op->d_TABl, la)
         LS3_DISPATCH(l, Z2);
@@ -443,7 +496,7 @@ int compact_spectrum3d(Op3D* op, const cd* d_gin, const int* d_fx, const int* d_
     }
     k_scale3<<<148 * 8, 256, 0, s>>>(G2, (long)slab2, 1.0 / (8.0 * (double)n * (double)m * (double)l));
     if (op->Cx > 1) {   // chunk-major unit order (Z is free by now and has the same size)
-        k_permute_units<<<148 * 16, 256, 0, s>>>(G2, Z, nel2 / 8, nel2 / op->Cx / 8, 2 * m, 2 * 8 * l);
+        k_permute_units<<<148 * 16, 256, 0, s>>>(G2, Z, nel2 / LBl, nel2 / op->Cx / LBl, 2 * m, 2 * LBl * l);
         std::swap(G2, Z);
     }
     LS_CUDA_TRY(cudaStreamSynchronize(s));
@@ -542,6 +595,7 @@ int create3d(ls_handle* out, int64_t n, int64_t m, int64_t l, int64_t ne, int64_
         if (compact) TRY(compact_spectrum3d(op, d_gin, d_fx, d_fy, d_fz, p));
         else {
             const long nc4 = nel / op->Cx;       // chunk-major spectrum: chunk c holds the x-slots [c*nc4, (c+1)*nc4) of the slab
+            p.lb = lines_b(l);
             for (int c = 0; c < op->Cx; ++c) {
                 p.nel = nc4; p.sx0 = (long)rank * nel + c * nc4;
                 k_fill_g3d<<<148 * 16, 256, 0, op->stream>>>(d_gin, op->d_G + (size_t)c * nc4 * me * le, d_fx, d_fy, d_fz, p);

@@ -24,8 +24,8 @@ import scipy.sparse as sp
 from .operators import FFTconvolution as _gpu_fftconvolution
 
 __all__ = ["createIndices", "sampleGConv", "sampleG3D", "entriesSparseAConv", "entriesSparseGConv",
-           "buildSparseAConv", "buildSparseAGConv", "entriesSparseA3D", "entriesSparseG3D",
-           "buildSparseA3DConv", "buildSparseAG3DConv"]
+           "buildSparseAConv", "buildSparseAGConv", "sparsifying_matrices_2d", "entriesSparseA3D", "entriesSparseG3D",
+           "buildSparseA3DConv", "buildSparseAG3DConv", "sparsifying_matrices_3d"]
 
 
 def createIndices(row, col, val):
@@ -37,6 +37,86 @@ def createIndices(row, col, val):
         raise AssertionError("length(col) == length(val)")
     Row = np.repeat(row, col.size)
     return Row, np.tile(col, row.size) + Row, np.tile(val, row.size)
+
+
+class _HostRows:
+    """Rows of G sampled through a host-visible apply (tests inject one): s x N array on the host."""
+
+    def __init__(self, rows, ind):
+        self.rows, self.ind = rows, np.asarray(ind, dtype=np.int64)
+
+    def null_vector(self):
+        """U[:, end]' of svd(rows[:, far]) - the stencil coefficients (SparsifyingMatrix2D.jl:119-127)."""
+        far = np.ones(self.rows.shape[1], dtype=bool)
+        far[self.ind - 1] = False
+        return _last_left_singular_vector(self.rows[:, far])
+
+    def block(self, perm=None):
+        """rows[:, ind] (optionally with rows and columns re-ordered by perm): G restricted to the stencil."""
+        B = self.rows[:, self.ind - 1]
+        return B if perm is None else B[np.ix_(perm, perm)]
+
+    def free(self):
+        self.rows = None
+
+
+class _DeviceRows:
+    """The same on the GPU (ls_sample_rows / ls_gram / ls_gather_rows): the s rows never leave the device; the far-field
+    Gram matrix GS GS^H = (full Gram) - (near block)(near block)^H comes back as s^2 numbers and its eigenvector of the
+    smallest eigenvalue is the last left singular vector of GS.  (Squaring costs accuracy: with sigma_min / sigma_max
+    ~ 1e-2..1e-3 for these blocks the coefficients are good to ~1e-10 instead of 1e-15 - immaterial for a preconditioner
+    whose stencils are defined up to a phase anyway)"""
+
+    def __init__(self, fastconv, N, ind, ws):
+        import ctypes as C
+        from ._lib import DeviceBuffer, check, lib, ptr
+        self.ind = np.ascontiguousarray(ind, dtype=np.int64)
+        self.s, self.N, self.ws = int(self.ind.size), int(N), ws
+        if self.ind.min() < 1 or self.ind.max() > N:
+            raise IndexError("stencil index outside the grid (grid too small for a 3-point stencil?)")
+        self.V = DeviceBuffer(16 * self.N * self.s)
+        check(lib().ls_sample_rows(ws.handle, fastconv.handle, ptr(self.ind), self.s, ptr(self.V), self.N))
+        self._B = None
+
+    def _near(self):
+        from ._lib import check, lib, ptr
+        if self._B is None:
+            B = np.empty((self.s, self.s), dtype=np.complex128)
+            check(lib().ls_gather_rows(self.ws.handle, ptr(self.V), self.N, self.s, ptr(self.ind), self.s, ptr(B)))
+            self._B = B
+        return self._B
+
+    def null_vector(self):
+        from ._lib import check, lib, ptr
+        g = np.empty((self.s, self.s), dtype=np.complex128)          # g[j, i] = sum_c conj(rows[i, c]) rows[j, c]
+        check(lib().ls_gram(self.ws.handle, ptr(self.V), self.N, self.s, ptr(g)))
+        B = self._near()
+        GG = g - B @ B.conj().T                                       # far-field GS GS^H (Hermitian)
+        GG = 0.5 * (GG + GG.conj().T)
+        w, U = np.linalg.eigh(GG)
+        return np.conj(U[:, 0])
+
+    def block(self, perm=None):
+        B = self._near()
+        return B if perm is None else B[np.ix_(perm, perm)]
+
+    def free(self):
+        if self.V is not None:
+            self.V.free()
+            self.V = None
+
+
+def _is_gpu_operator(fastconv):
+    return hasattr(fastconv, "handle") and hasattr(fastconv, "_apply")
+
+
+def _sampler(fastconv, N, apply):
+    """Row sampler for one sparsifier build: device-resident when the operator is a GPU handle and no apply is injected."""
+    if apply is None and _is_gpu_operator(fastconv):
+        from .krylov import KrylovWorkspace
+        ws = KrylovWorkspace(N)
+        return lambda ind: _DeviceRows(fastconv, N, ind, ws)
+    return lambda ind: _HostRows(_sample_rows(fastconv, N, ind, apply), ind)
 
 
 def _sample_rows(fastconv, N, indS, apply):
@@ -115,32 +195,29 @@ def sampleG3D(k, X, Y, Z, indS, fastconv, apply=None):
 
 
 def _sample_classes_3d(fastconv, n, m, l, apply):
-    """One sampling per class, shared by entriesSparseA3D and entriesSparseG3D: (rel, ind, rows)."""
+    """One sampling per class, shared by entriesSparseA3D and entriesSparseG3D: (rel, null vector, stencil block).
+    With a GPU operator the rows are sampled, reduced (Gram matrix) and dropped class by class on the device."""
     out = []
+    sample = _sampler(fastconv, n * m * l, apply)
     for cls in _CLASSES_3D:
         rel = _rel3(cls, n, m)
         ind = _centre3(cls, n, m, l) + rel
-        out.append((rel, ind, _sample_rows(fastconv, n * m * l, ind, apply)))
+        rows = sample(ind)
+        out.append((rel, rows.null_vector(), rows.block()))
+        rows.free()
     return out
 
 
 def entriesSparseA3D(k, X, Y, Z, fastconv, n, m, l, apply=None, _samples=None):
     """SparsifyingMatrix3D.jl:1136-1408 -> (Indices, Entries)."""
     samples = _samples if _samples is not None else _sample_classes_3d(fastconv, n, m, l, apply)
-    N = n * m * l
-    Indices, Entries = [], []
-    for rel, ind, rows in samples:
-        far = np.ones(N, dtype=bool)
-        far[ind - 1] = False
-        Entries.append(_last_left_singular_vector(rows[:, far]))
-        Indices.append(rel)
-    return Indices, Entries
+    return [rel for rel, v, blk in samples], [v for rel, v, blk in samples]
 
 
 def entriesSparseG3D(k, X, Y, Z, fastconv, n, m, l, apply=None, _samples=None):
     """SparsifyingMatrix3D.jl:963-1135: G restricted to each class's own stencil."""
     samples = _samples if _samples is not None else _sample_classes_3d(fastconv, n, m, l, apply)
-    return [rows[:, ind - 1] for rel, ind, rows in samples]
+    return [blk for rel, v, blk in samples]
 
 
 def buildSparseA3DConv(k, X, Y, Z, fastconv, n, m, l, apply=None, _samples=None):
@@ -222,27 +299,33 @@ def _rows2(n, m):
             Ind[0, 0], Ind[-1, 0], Ind[0, -1], Ind[-1, -1]]
 
 
-def entriesSparseAConv(k, X, Y, fastconv, n, m, apply=None, strict=True):
-    """SparsifyingMatrix2D.jl:104-201 -> (Indices, Entries)."""
-    N = n * m
-    Indices, Entries = [], []
-    for centre, relA, relG in _classes_2d(n, m, strict):
-        ind = centre + relA
-        rows = _sample_rows(fastconv, N, ind, apply)
-        far = np.ones(N, dtype=bool)
-        far[ind - 1] = False
-        Entries.append(_last_left_singular_vector(rows[:, far]))
-        Indices.append(np.asarray(relA, dtype=np.int64))
-    return Indices, Entries
-
-
-def entriesSparseGConv(k, X, Y, fastconv, n, m, apply=None, strict=True):
-    """SparsifyingMatrix2D.jl:278-350."""
+def _sample_classes_2d(fastconv, n, m, apply, strict):
+    """One sampling pass over the 9 boundary classes: (relA, null vector, G block in entriesSparseGConv's stencil order).
+    The edge orderings of entriesSparseGConv (:293-304) are permutations of entriesSparseAConv's stencils, so the block
+    G[indG, indG] is the sampled block G[indA, indA] re-ordered - no second round of applies."""
     out = []
+    sample = _sampler(fastconv, n * m, apply)
     for centre, relA, relG in _classes_2d(n, m, strict):
-        ind = centre + relG
-        out.append(_sample_rows(fastconv, n * m, ind, apply)[:, ind - 1])
+        relA = np.asarray(relA, dtype=np.int64)
+        relG = np.asarray(relG, dtype=np.int64)
+        pos = {int(r): i for i, r in enumerate(relA)}
+        perm = np.array([pos[int(r)] for r in relG], dtype=np.int64)
+        rows = sample(centre + relA)
+        out.append((relA, rows.null_vector(), rows.block(perm)))
+        rows.free()
     return out
+
+
+def entriesSparseAConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _samples=None):
+    """SparsifyingMatrix2D.jl:104-201 -> (Indices, Entries)."""
+    samples = _samples if _samples is not None else _sample_classes_2d(fastconv, n, m, apply, strict)
+    return [rel for rel, v, blk in samples], [v for rel, v, blk in samples]
+
+
+def entriesSparseGConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _samples=None):
+    """SparsifyingMatrix2D.jl:278-350."""
+    samples = _samples if _samples is not None else _sample_classes_2d(fastconv, n, m, apply, strict)
+    return [blk for rel, v, blk in samples]
 
 
 def buildSparseAConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _cache=None):
@@ -251,9 +334,22 @@ def buildSparseAConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _cache=No
     return _assemble(n * m, _rows2(n, m), Indices, Values)
 
 
-def buildSparseAGConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _cache=None):
+def buildSparseAGConv(k, X, Y, fastconv, n, m, apply=None, strict=True, _cache=None, _samples=None):
     """SparsifyingMatrix2D.jl:441-532: rows Values[c] * Entries[c]."""
-    Indices, Values = _cache if _cache is not None else entriesSparseAConv(k, X, Y, fastconv, n, m, apply, strict)
-    Entries = entriesSparseGConv(k, X, Y, fastconv, n, m, apply, strict)
+    if _samples is not None:
+        Indices, Values = entriesSparseAConv(k, X, Y, fastconv, n, m, apply, strict, _samples)
+    else:
+        Indices, Values = _cache if _cache is not None else entriesSparseAConv(k, X, Y, fastconv, n, m, apply, strict)
+    Entries = entriesSparseGConv(k, X, Y, fastconv, n, m, apply, strict, _samples)
+    # literal upstream: ValuesAG = Values[c] * Entries[c] (:456-532) - on the four edges Values follows entriesSparseAConv's
+    # stencil order and Entries entriesSparseGConv's (:293-304); the mismatch is the reference's and is kept
     ValuesAG = [np.asarray(v).reshape(1, -1) @ e for v, e in zip(Values, Entries)]
     return _assemble(n * m, _rows2(n, m), Indices, ValuesAG)
+
+
+def sparsifying_matrices_2d(k, X, Y, fastconv, n, m, nu, apply=None, strict=True):
+    """examples/example.jl:64-67 with the *Conv builders, in one sampling pass: (As, Mapproxsp = As + k^2 AG diag(nu))."""
+    samples = _sample_classes_2d(fastconv, n, m, apply, strict)
+    As = buildSparseAConv(k, X, Y, fastconv, n, m, apply, strict, _cache=entriesSparseAConv(k, X, Y, fastconv, n, m, apply, strict, samples))
+    AG = buildSparseAGConv(k, X, Y, fastconv, n, m, apply, strict, _samples=samples)
+    return As, (As + k ** 2 * (AG @ sp.diags(np.asarray(nu, dtype=np.float64)))).tocsc()

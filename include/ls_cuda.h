@@ -199,6 +199,15 @@ int ls_gmres_msp(ls_handle krylov, ls_handle op, ls_handle As, ls_handle msp,
 /* wall time the last ls_gmres spent in D2H + msp_solve callback + H2D (the "Msp-solve" column of SURVEY.md H1) */
 int ls_krylov_last_precond_host_seconds(ls_handle krylov, double* seconds);
 
+/* ---- sparsifier sampling on the device: sampleGConv (FastConvolution.jl:278-306), sampleG3D (FastConvolution3D.jl:136-160).
+ * V[:, i] = FFTconvolution(op, e_{indS[i]}) for the s stencil indices (1-based), kept on the device (N x s, column-major).   */
+int ls_sample_rows(ls_handle krylov, ls_handle op, const int64_t* indS, int s, ls_cdouble* V_dev, int64_t ldv);
+/* gram[i + s*j] = sum_c conj(V[c,i]) V[c,j] (host, s x s): what entriesSparseAConv's svd(GSampled) needs of the rows
+ * (SparsifyingMatrix2D.jl:119-127) - its last left singular vector is the eigenvector of the smallest eigenvalue.   */
+int ls_gram(ls_handle krylov, const ls_cdouble* V_dev, int64_t ldv, int s, ls_cdouble* gram_host);
+/* out[j + nidx*i] = V[idx[j], i] (idx 1-based): the near-field block sampleGConv(...)[:, ind] of entriesSparseGConv (:278-350) */
+int ls_gather_rows(ls_handle krylov, const ls_cdouble* V_dev, int64_t ldv, int s, const int64_t* idx, int nidx, ls_cdouble* out_host);
+
 /* ---- handle services ------------------------------------------------------------------ */
 int ls_destroy(ls_handle h);
 int ls_sync(ls_handle h);

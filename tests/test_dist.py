@@ -18,6 +18,7 @@ def _torchrun(nproc, args, port, timeout=600):
            "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER] + args
     env = dict(os.environ)
     env.setdefault("OMP_NUM_THREADS", "2")
+    env.setdefault("LS_ORACLE_WORKERS", str(max(1, (os.cpu_count() or 1) // nproc)))    # every rank evaluates the oracle
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 

@@ -130,7 +130,7 @@ def test_spectrum_generated_on_the_device(n, m):
     h = 1.0 / n
     x = -0.5 + h * np.arange(n)
     y = -0.5 * m / n + h * np.arange(m)
-    k = 2 * np.pi / (10 * h)
+    k = 2 * np.pi / (8.3 * h)          # 10 points per wavelength puts grid frequencies exactly on s == k at n = 100 (Q7: NaN upstream)
     Mo = O.buildFastConvolution(x, y, h, k, O.nu_gaussian_2d, quadRule="Greengard_Vico")
     # L, Lp exactly as buildFastConvolution takes them (FastConvolution.jl:187-188)
     Lp = 4.0 * (x[-1] - x[0] + h)
@@ -145,3 +145,22 @@ def test_spectrum_generated_on_the_device(n, m):
     assert _rel(Mg * b, Mh * b) < 1e-13
     with pytest.raises(ValueError):
         ls.FastM(None, Mo.nu, 4 * n, 4 * m, n, m, k, quadRule="Greengard_Vico")          # needs L, Lp
+
+
+def test_q7_grid_frequency_on_the_wave_number_is_guarded():
+    """Q7: Gtruncated2D divides by s^2 - k^2; at n = 100 with 10 points per wavelength the lattice points (40, 0), (24, 32), ...
+    sit exactly on s == k and the reference's spectrum holds NaN there.  The device generator moves such a frequency by
+    sqrt(eps) (removable singularity), so the operator stays finite - and equals the host-built one wherever that is finite."""
+    import fast_solver_lippmann_schwinger_b200 as ls
+    from fast_solver_lippmann_schwinger_b200.problems import gv_spectrum_2d, nu_gaussian_2d
+    n = 100
+    h = 1.0 / n
+    k = 2 * np.pi / (10 * h)
+    G = gv_spectrum_2d(n, n, h, k)
+    assert not np.isfinite(G).all()
+    x = -0.5 + h * np.arange(n)
+    X = np.repeat(x[:, None], n, axis=1).reshape(-1, order="F")
+    Y = np.repeat(x[None, :], n, axis=0).reshape(-1, order="F")
+    M = ls.FastM(None, nu_gaussian_2d(X, Y), 4 * n, 4 * n, n, n, k, quadRule="Greengard_Vico", L=1.5 * n * h, Lp=4.0 * n * h)
+    b = np.random.default_rng(0).standard_normal(n * n) + 0j
+    assert np.isfinite(M * b).all()

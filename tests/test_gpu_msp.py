@@ -148,3 +148,43 @@ def test_gmres_maxiter_semantics_follow_upstream():
     assert _rel(xg, xo) < 1e-10                                    # both hold the iterate of the restart at 5
     x5, _ = ls.gmres_(x0.copy(), Mg, rhs, restart=5, maxiter=5, reltol=1e-14, log=True)
     assert _rel(xg, x5) < 1e-12
+
+
+def test_sparsifier2d_sampled_and_reduced_on_the_device():
+    """SURVEY 8(f) row 2 in 2-D: buildSparseAConv / buildSparseAGConv (SparsifyingMatrix2D.jl:104-201, 278-350, 441-532, 888-966)
+    with the 49 unit-vector FFTconvolution applies, the rows and their far-field Gram matrices kept on the GPU
+    (ls_sample_rows / ls_gram / ls_gather_rows) against the oracle's QR + SVD of the host-sampled rows, up to the per-row
+    phase (Q5); then the whole preconditioned solve on the device with these matrices."""
+    from oracle import ls_oracle as O
+    import fast_solver_lippmann_schwinger_b200 as ls
+    from fast_solver_lippmann_schwinger_b200 import sparsifier as S
+    n = 64
+    h = 1.0 / n
+    x = -0.5 + h * np.arange(n)
+    k = 2 * np.pi / (8.3 * h)
+    Mo = O.buildFastConvolution(x, x, h, k, O.nu_gaussian_2d, quadRule="Greengard_Vico")
+    X, Y = O.grid2d(x, x)
+    cache = O.entriesSparseAConv(k, X, Y, Mo, n, n, strict=False)
+    As_o = O.buildSparseAConv(k, X, Y, Mo, n, n, strict=False, _cache=cache)
+    AG_o = O.buildSparseAGConv(k, X, Y, Mo, n, n, strict=False, _cache=cache)
+    Msp_o = (As_o + k ** 2 * (AG_o @ sp.diags(Mo.nu))).tocsc()
+    Mg = ls.FastM(Mo.GFFT, Mo.nu, Mo.ne, Mo.me, n, n, k, quadRule="Greengard_Vico")
+    l0 = Mg.launch_count()
+    As, Msp = S.sparsifying_matrices_2d(k, X, Y, Mg, n, n, Mo.nu, strict=False)
+    assert Mg.launch_count() - l0 == 3 * (9 + 4 * 6 + 4 * 4)          # one sampling pass: 49 applies of three kernels
+    A, B = As.tocsr(), As_o.tocsr()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+    for r in range(0, A.shape[0], 13):
+        a, b = A.data[A.indptr[r]:A.indptr[r + 1]], B.data[B.indptr[r]:B.indptr[r + 1]]
+        ph = np.vdot(b, a) / abs(np.vdot(b, a))
+        assert np.abs(a - ph * b).max() <= 1e-7 * np.abs(b).max(), r
+    v = np.random.default_rng(5).standard_normal(n * n) + 0j
+    w_o = spla.splu(Msp_o).solve(As_o @ v)
+    assert _rel(spla.splu(Msp).solve(As @ v), w_o) < 1e-6
+    P = ls.SparsifyingPreconditioner(Msp, As, solverType="GPU", grid=(n, n))
+    assert _rel(P.solve(v), w_o) < 1e-6
+    u_inc = np.exp(1j * k * X)
+    rhs = -(Mg * u_inc - u_inc)
+    u, hist = ls.gmres_(np.zeros(n * n, complex), Mg, rhs, Pl=P, log=True, reltol=1e-8)
+    assert hist.isconverged
+    assert np.linalg.norm((Mg * u) - rhs) / np.linalg.norm(rhs) < 1e-6
