@@ -12,7 +12,7 @@ import re
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libls_cuda.so")
+LIB_PATH = os.environ.get("LS_CUDA_LIB") or os.path.join(HERE, "lib", "libls_cuda.so")     # LS_CUDA_LIB: another build of the same library
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "ls_cuda.h")
 
 LS_OK = 0

@@ -20,7 +20,14 @@ std::vector<int> slot_freq(int N) {
         case 64:   E = 8;  S = 2; R[0] = 8;  R[1] = 8;  R[2] = 1;  break;
         case 128:  E = 16; S = 2; R[0] = 16; R[1] = 8;  R[2] = 1;  break;
         case 256:  E = 16; S = 2; R[0] = 16; R[1] = 16; R[2] = 1;  break;
-        case 512:  E = 8;  S = 3; R[0] = 8;  R[1] = 8;  R[2] = 8;  break;
+        case 512: {
+            // 16 x 16 x 2 with the closing radix-2 across lane partners (fft_engine.cuh ShflLast): thread t, register e holds
+            // the frequency d0 + 16 d1 + 256 d2 with d0 = t / 2 (stage-0 output), d1 = e (stage-1 output), d2 = t & 1
+            std::vector<int> f(512);
+            for (int t = 0; t < 32; ++t)
+                for (int e = 0; e < 16; ++e) f[t + 32 * e] = (t / 2) + 16 * e + 256 * (t & 1);
+            return f;
+        }
         case 1024: E = 16; S = 3; R[0] = 16; R[1] = 8;  R[2] = 8;  break;
         case 2048: E = 16; S = 3; R[0] = 16; R[1] = 16; R[2] = 8;  break;
         case 4096: E = 16; S = 3; R[0] = 16; R[1] = 16; R[2] = 16; break;
@@ -77,7 +84,7 @@ std::vector<cd> engine_table(int N) {
         case 64:   E = 8;  S = 2; R0 = 8;  R1 = 8;  break;
         case 128:  E = 16; S = 2; R0 = 16; R1 = 8;  break;
         case 256:  E = 16; S = 2; R0 = 16; R1 = 16; break;
-        case 512:  E = 8;  S = 3; R0 = 8;  R1 = 8;  break;
+        case 512:  E = 16; S = 3; R0 = 16; R1 = 16; break;
         case 1024: E = 16; S = 3; R0 = 16; R1 = 8;  break;
         case 2048: E = 16; S = 3; R0 = 16; R1 = 16; break;
         case 4096: E = 16; S = 3; R0 = 16; R1 = 16; break;

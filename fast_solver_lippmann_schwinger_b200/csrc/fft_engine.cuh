@@ -147,12 +147,19 @@ template <int N> struct Cfg;
 template <> struct Cfg<64>   { static constexpr int E = 8,  S = 2, R0 = 8,  R1 = 8,  R2 = 1; };
 template <> struct Cfg<128>  { static constexpr int E = 16, S = 2, R0 = 16, R1 = 8,  R2 = 1; };
 template <> struct Cfg<256>  { static constexpr int E = 16, S = 2, R0 = 16, R1 = 16, R2 = 1; };
-template <> struct Cfg<512>  { static constexpr int E = 8,  S = 3, R0 = 8,  R1 = 8,  R2 = 8; };
+// 512 = 16 x 16 x 2: the closing radix-2 stage pairs values that sit in lane partners t, t^1 at the same register index
+// (addresses 32 D + 2a + b after stage 1, b = t & 1), so it runs on warp shuffles: one shared-memory exchange and one
+// barrier per transform instead of the two of the former 8 x 8 x 8 plan (the 512-point z / y passes of the 512^3 apply
+// were shared-memory bound at 47-56 % of the HBM roofline).
+template <> struct Cfg<512>  { static constexpr int E = 16, S = 3, R0 = 16, R1 = 16, R2 = 2; };
 template <> struct Cfg<1024> { static constexpr int E = 16, S = 3, R0 = 16, R1 = 8,  R2 = 8; };
 template <> struct Cfg<2048> { static constexpr int E = 16, S = 3, R0 = 16, R1 = 16, R2 = 8; };
 template <> struct Cfg<4096> { static constexpr int E = 16, S = 3, R0 = 16, R1 = 16, R2 = 16; };
 
 constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
+// the last stage is a radix-2 done across lane partners (no shared-memory exchange in front of it)
+template <int N> struct ShflLast { static constexpr bool value = (Cfg<N>::S == 3 && Cfg<N>::R2 == 2); };
 
 template <int N, int I> struct Stage {
     typedef Cfg<N> C;
@@ -177,10 +184,19 @@ template <int N, int I> struct Stage {
 // shared-memory layouts --------------------------------------------------------------
 // A: one line contiguous at `base`, XOR swizzle keyed on the last radix
 template <int N> struct LayA {
+    static constexpr int XOR_LANE = 1;           // lane distance of the threads t, t^1 of one line
     int base;
     __device__ __forceinline__ int phys(int l) const {
-        constexpr int sh = ilog2(Stage<N, 0>::RLAST);
-        return base + (l ^ ((l >> sh) & 7));
+        if constexpr (ShflLast<N>::value) {
+            // only stages 0 and 1 touch shared memory.  Stage 1 reads 32 D + 2a + b with D = t/2, b = t&1: the four D of a
+            // quarter warp would hit the same eight banks; XOR bits 1-2 with D mod 4 spreads them (stage 0, 32a + t, only
+            // sees a permutation inside aligned groups of eight)
+            constexpr int sh = ilog2(Stage<N, 1>::Mprev);
+            return base + (l ^ (((l >> sh) & 3) << 1));
+        } else {
+            constexpr int sh = ilog2(Stage<N, 0>::RLAST);
+            return base + (l ^ ((l >> sh) & 7));
+        }
     }
 };
 // B: LB adjacent lines interleaved point by point (lane % LB = line).  LB = 8: a quarter warp reads one point of eight
@@ -188,12 +204,16 @@ template <int N> struct LayA {
 // threads per CTA, so two CTAs fit an SM): a quarter warp spans two points t, t+1 (t even) of four lines, i.e. two
 // 64-byte pieces that must fall into different halves of the 32 banks - true when the two logical addresses differ in
 // parity, which the XOR with bit log2(RLAST) arranges for the last stage (addresses 8t + a and 8(t+1) + a there).
-template <int N> struct LinesB { static constexpr int value = (N == 512) ? 4 : 8; };
+#ifndef LS_LINESB512
+#define LS_LINESB512 4
+#endif
+template <int N> struct LinesB { static constexpr int value = (N == 512) ? LS_LINESB512 : 8; };
 template <int N> struct LayB {
     static constexpr int LB = LinesB<N>::value;
+    static constexpr int XOR_LANE = LB;          // lane = t * LB + line
     int lam;
     __device__ __forceinline__ int phys(int l) const {
-        if (LB == 8) return l * 8 + lam;
+        if (LB == 8 || ShflLast<N>::value) return l * LB + lam;     // stages 0 / 1 of the shuffle plan: l, l+1 for t, t+1
         constexpr int sh = ilog2(Stage<N, 0>::RLAST);
         return (l ^ ((l >> sh) & 1)) * LB + lam;
     }
@@ -406,6 +426,21 @@ __device__ __forceinline__ void inv_stage(cd* v, int t, const TwState<N>& tw) {
 
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
+// closing / opening radix-2 stage of the shuffle plans: thread t (even) holds p = value at address 2D, its partner
+// t^1 holds q at 2D + 1, for every register index a.  Forward and adjoint are the same butterfly: even keeps p + q,
+// odd keeps p - q.
+template <int N, class Lay>
+__device__ __forceinline__ void shfl_radix2(cd* v, int t) {
+    constexpr int E = Cfg<N>::E;
+    const bool odd = (t & 1) != 0;
+#pragma unroll
+    for (int a = 0; a < E; ++a) {
+        const double qx = __shfl_xor_sync(0xffffffffu, v[a].x, Lay::XOR_LANE);
+        const double qy = __shfl_xor_sync(0xffffffffu, v[a].y, Lay::XOR_LANE);
+        v[a] = odd ? make_double2(qx - v[a].x, qy - v[a].y) : make_double2(v[a].x + qx, v[a].y + qy);
+    }
+}
+
 // Forward FFT of sub-transform r of one line.  In: v[a] = x[a*T + t].  Out: v[e] = X_r[freq(t + T*e)],
 // X_r = FFT_N(x[j] w_{4N}^{r j}).  sm/lay = this line's exchange buffer (N points).
 // `pre_last` runs on every thread just before the butterflies of the last stage (the place to issue
@@ -418,7 +453,11 @@ __device__ __forceinline__ void fft_fwd(cd* v, int t, int r, cd* sm, const Lay& 
     st_stage<N, 0>(v, t, sm, lay);
     __syncthreads();
     ld_stage<N, 1>(v, t, sm, lay);
-    if constexpr (C::S == 3) {
+    if constexpr (ShflLast<N>::value) {
+        pre_last();                      // the closing stage is a handful of shuffles: issue the loads ahead of stage 1
+        fwd_stage<N, 1>(v, t, tw);
+        shfl_radix2<N, Lay>(v, t);
+    } else if constexpr (C::S == 3) {
         fwd_stage<N, 1>(v, t, tw);
         st_stage<N, 1>(v, t, sm, lay);
         __syncthreads();
@@ -438,7 +477,13 @@ template <int N, class Lay, class Hook = NoHook>
 __device__ __forceinline__ void fft_inv(cd* v, int t, int r, cd* sm, const Lay& lay, const TwState<N>& tw,
                                         Hook hook = Hook()) {
     typedef Cfg<N> C;
-    if constexpr (C::S == 3) {
+    if constexpr (ShflLast<N>::value) {
+        shfl_radix2<N, Lay>(v, t);
+        inv_stage<N, 1>(v, t, tw);
+        st_stage<N, 1>(v, t, sm, lay);
+        __syncthreads();
+        hook();
+    } else if constexpr (C::S == 3) {
         inv_stage<N, 2>(v, t, tw);
         st_stage<N, 2>(v, t, sm, lay);
         __syncthreads();

@@ -81,6 +81,32 @@ __device__ __forceinline__ void block_finish(double sx, double sy, double2* part
     }
 }
 
+// ---- L2 residency hints (LS_MGS_L2HINT=1, experiment) --------------------------------------------------------------
+// A modified Gram-Schmidt sweep re-reads and re-writes w in every one of its k steps while the basis columns stream by
+// once each.  At 2048^2 w is 67 MB against 126 MB of L2: loading / storing w with an evict_last policy and the basis
+// columns with evict_first asks the L2 to keep w resident across the sweep (64 -> 32 bytes of HBM traffic per element
+// and step if it does).
+__device__ __forceinline__ unsigned long long l2_policy_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <bool HINT> __device__ __forceinline__ cd ld_pol(const cd* p, unsigned long long pol) {
+    if (!HINT) return *p;
+    cd v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+template <bool HINT> __device__ __forceinline__ void st_pol(cd* p, cd v, unsigned long long pol) {
+    if (!HINT) { *p = v; return; }
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
 // h = conj(x) . y
 __global__ void __launch_bounds__(RED_THREADS)
 k_dot(const cd* __restrict__ x, const cd* __restrict__ y, long n, double2* partials, unsigned* ticket,
@@ -107,19 +133,21 @@ k_nrm2(const cd* __restrict__ x, long n, double2* partials, unsigned* ticket, do
 }
 
 // w -= h_prev * vprev ;  h = conj(vi) . w
+template <bool HINT>
 __global__ void __launch_bounds__(RED_THREADS)
 k_axpy_dot(const cd* __restrict__ vprev, const double* hprev_re, const double* hprev_im,
            const cd* __restrict__ vi, cd* w, long n, double2* partials, unsigned* ticket,
            double* out_re, double* out_im) {
     const double hr = *hprev_re, hi = *hprev_im;
+    const unsigned long long keep = HINT ? l2_policy_last() : 0ull, stream = HINT ? l2_policy_first() : 0ull;
     double sx = 0.0, sy = 0.0;
     for (long i = (long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long)gridDim.x * RED_THREADS) {
-        const cd p = vprev[i];
-        cd ww = w[i];
+        const cd p = ld_pol<HINT>(&vprev[i], stream);
+        cd ww = ld_pol<HINT>(&w[i], keep);
         ww.x -= hr * p.x - hi * p.y;
         ww.y -= hr * p.y + hi * p.x;
-        w[i] = ww;
-        const cd a = vi[i];
+        st_pol<HINT>(&w[i], ww, keep);
+        const cd a = ld_pol<HINT>(&vi[i], stream);
         sx += a.x * ww.x + a.y * ww.y;
         sy += a.x * ww.y - a.y * ww.x;
     }
@@ -127,17 +155,19 @@ k_axpy_dot(const cd* __restrict__ vprev, const double* hprev_re, const double* h
 }
 
 // w -= h_prev * vprev ;  out = sqrt(sum |w|^2)
+template <bool HINT>
 __global__ void __launch_bounds__(RED_THREADS)
 k_axpy_nrm2(const cd* __restrict__ vprev, const double* hprev_re, const double* hprev_im, cd* w, long n,
             double2* partials, unsigned* ticket, double* out, int take_sqrt) {
     const double hr = *hprev_re, hi = *hprev_im;
+    const unsigned long long keep = HINT ? l2_policy_last() : 0ull, stream = HINT ? l2_policy_first() : 0ull;
     double sx = 0.0;
     for (long i = (long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long)gridDim.x * RED_THREADS) {
-        const cd p = vprev[i];
-        cd ww = w[i];
+        const cd p = ld_pol<HINT>(&vprev[i], stream);
+        cd ww = ld_pol<HINT>(&w[i], keep);
         ww.x -= hr * p.x - hi * p.y;
         ww.y -= hr * p.y + hi * p.x;
-        w[i] = ww;
+        st_pol<HINT>(&w[i], ww, keep);
         sx += ww.x * ww.x + ww.y * ww.y;
     }
     block_finish(sx, 0.0, partials, ticket, out, nullptr, take_sqrt);
@@ -332,14 +362,24 @@ struct Krylov : HandleBase {
             if ((rc = nrm2(w, h, s))) return rc;
             cudaMemsetAsync(h + 1, 0, sizeof(double), s);
         } else {
+            static int l2hint = -1;
+            if (l2hint < 0) { const char* e = getenv("LS_MGS_L2HINT"); l2hint = e ? atoi(e) : 0; }
             if ((rc = dot(V, w, h, s))) return rc;
             for (int i = 1; i < k; ++i) {
-                k_axpy_dot<<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(i - 1) * ldv, h + 2 * (i - 1), h + 2 * (i - 1) + 1,
-                                                              V + (long)i * ldv, w, n, d_partials, d_ticket, h + 2 * i, h + 2 * i + 1);
+                if (l2hint)
+                    k_axpy_dot<true><<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(i - 1) * ldv, h + 2 * (i - 1), h + 2 * (i - 1) + 1,
+                                                                        V + (long)i * ldv, w, n, d_partials, d_ticket, h + 2 * i, h + 2 * i + 1);
+                else
+                    k_axpy_dot<false><<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(i - 1) * ldv, h + 2 * (i - 1), h + 2 * (i - 1) + 1,
+                                                                         V + (long)i * ldv, w, n, d_partials, d_ticket, h + 2 * i, h + 2 * i + 1);
                 launches++;
                 if ((rc = allreduce(h + 2 * i, 2, s))) return rc;
             }
-            k_axpy_nrm2<<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(k - 1) * ldv, h + 2 * (k - 1), h + 2 * (k - 1) + 1, w, n,
+            if (l2hint)
+                k_axpy_nrm2<true><<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(k - 1) * ldv, h + 2 * (k - 1), h + 2 * (k - 1) + 1, w, n,
+                                                                     d_partials, d_ticket, h + 2 * k, comm ? 0 : 1);
+            else
+            k_axpy_nrm2<false><<<RED_BLOCKS, RED_THREADS, 0, s>>>(V + (long)(k - 1) * ldv, h + 2 * (k - 1), h + 2 * (k - 1) + 1, w, n,
                                                            d_partials, d_ticket, h + 2 * k, comm ? 0 : 1);
             launches++;
             if ((rc = finish_norm(h + 2 * k, s))) return rc;

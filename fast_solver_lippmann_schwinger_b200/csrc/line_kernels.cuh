@@ -35,9 +35,17 @@ template <int N> struct GeoB {
 };
 // resident CTAs per SM asked of ptxas: 128-thread CTAs 3 (168 registers); the 256-thread CTAs of the 4-line mode-B
 // geometry 2 (128 registers: E = 8 points per thread there); everything else 1
+#ifndef LS_INV512_MINB
+#define LS_INV512_MINB 2        // measured (profiles/r2_l_512_variants.log): 512^3 P4 3.67 -> 3.19 ms, 2-D 512^2 apply 0.0353 -> 0.0332 ms
+#endif
 template <int N, bool MODE_B> struct MinB {
     static constexpr int TH = MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS;
     static constexpr int value = (TH <= 128) ? 3 : ((MODE_B && GeoB<N>::LB == 4 && TH == 256) ? 2 : 1);
+};
+// the inverse pass keeps E accumulators next to the E working values: at 512 points (E = 16 since r2) the 168-register
+// cap of three CTAs per SM spills inside the loop
+template <int N, bool MODE_B> struct MinBInv {
+    static constexpr int value = (N == 512 && MinB<N, MODE_B>::value == 3) ? LS_INV512_MINB : MinB<N, MODE_B>::value;
 };
 
 // thread -> (line within CTA, thread within line, smem layout)
@@ -392,7 +400,7 @@ template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // cp.async while the current block is transformed (each thread stages exactly the elements it consumes: no
 // extra barrier), which takes two of the kernel's three exposed DRAM latencies off the critical path.
 template <int N, bool MODE_B, int PF = 0>
-__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MinB<N, MODE_B>::value)
+__global__ void __launch_bounds__(MODE_B ? GeoB<N>::THREADS : GeoA<N>::THREADS, MinBInv<N, MODE_B>::value)
 k_inv_pruned(const cd* __restrict__ in, const cd* bsrc, cd* out, const cd* __restrict__ TAB, double scale,
              const LineAddr la, long line0) {
     typedef Map<N, MODE_B> M;

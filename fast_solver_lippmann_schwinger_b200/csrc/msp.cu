@@ -55,7 +55,16 @@ struct Msp : MspBase {
     double factor_seconds = 0.0;
     cublasHandle_t cublas = nullptr;
     int solve_dev(const cd* rhs, cd* out, cudaStream_t s) override;
-    ~Msp() override { if (cublas) cublasDestroy(cublas); }
+    int solve_launch(const cd* rhs, cd* out, cudaStream_t s);
+    // the 4 x (depth + 1) dependent launches of one solve, captured once per (rhs, out) pair and replayed as a CUDA graph
+    // (GMRES calls the solve with at most restart + 2 different pairs): removes the launch gaps between the small kernels
+    struct Captured { const cd* rhs; cd* out; cudaGraphExec_t exec; };
+    std::vector<Captured> graphs;
+    int use_graph = -1;
+    ~Msp() override {
+        for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+        if (cublas) cublasDestroy(cublas);
+    }
 };
 
 // ---- solve kernels ------------------------------------------------------------------------------------------
@@ -543,6 +552,39 @@ int msp_factor(Msp* M, int n, int m, const int64_t* colptr, const int64_t* rowva
 }  // namespace
 
 int Msp::solve_dev(const cd* rhs, cd* out, cudaStream_t s) {
+    if (use_graph < 0) { const char* e = getenv("LS_MSP_GRAPH"); use_graph = e ? atoi(e) : 1; }
+    if (!use_graph) return solve_launch(rhs, out, s);
+    for (auto& g : graphs)
+        if (g.rhs == rhs && g.out == out) {
+            LS_CUDA_TRY(cudaGraphLaunch(g.exec, s));
+            launches += launches_per_solve;
+            return LS_OK;
+        }
+    if (graphs.size() >= 64) return solve_launch(rhs, out, s);
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        use_graph = 0;
+        return solve_launch(rhs, out, s);
+    }
+    const int rc = solve_launch(rhs, out, s);
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != LS_OK || ce != cudaSuccess || graph == nullptr) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        use_graph = 0;
+        return solve_launch(rhs, out, s);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); use_graph = 0; return solve_launch(rhs, out, s); }
+    graphs.push_back(Captured{rhs, out, exec});
+    LS_CUDA_TRY(cudaGraphLaunch(exec, s));
+    return LS_OK;
+}
+
+int Msp::solve_launch(const cd* rhs, cd* out, cudaStream_t s) {
     const int D = (int)lev.size() - 1;
     // upward pass: leaves -> root
     for (int d = D; d >= 0; --d) {

@@ -142,7 +142,7 @@ template <int N> int launch_mid_swap_op(Op2D* op) {
     // (168-register cap -> spills, and 3 x 66 KB of shared memory leaves 30 KB of L1 for the strided line loads:
     // 2048^2 0.297 vs 0.211 ms); at N <= 512 several lines share a CTA and three CTAs win (512^2 0.0189 vs 0.0194 ms).
     if (minb < 0) { const char* e = getenv("LS_P2_MINB"); minb = e ? atoi(e) : 0; }
-    const int use_minb = minb ? minb : (N <= 512 ? 3 : 2);
+    const int use_minb = minb ? minb : (N <= 256 ? 3 : 2);      // 16 points per thread from N = 512 up
     constexpr int MB = (GeoA<N>::THREADS <= 128 ? 3 : 1);
     op->phase_begin(1);
     cudaError_t e;

@@ -90,7 +90,7 @@ struct Op3D : HandleBase {
     }
 };
 
-inline int lines_b(long N) { return N == 512 ? 4 : 8; }      // LinesB<N> of the mode-B kernels (fft_engine.cuh)
+inline int lines_b(long N) { return N == 512 ? LS_LINESB512 : 8; }      // LinesB<N> of the mode-B kernels (fft_engine.cuh)
 
 struct GenParams {
     int lb = 8;         // x-adjacent z lines interleaved per spectrum unit
