@@ -401,7 +401,14 @@ __device__ __forceinline__ void fwd_stage(cd* v, int t, const TwState<N>& tw) {
 #pragma unroll
             for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmul(v[u * St::R + d], tw.tw1[d * St::M + b]);
 #else
-            mul_twiddle_powers<St::R, false>(v + u * St::R, tw.tw1[St::M + b]);
+            if constexpr (false && St::M == 2) {   // measured slower (divergent constant-bank reads): 512^3 apply 18.7 -> 19.4 ms; the product tree stays
+                // w_Mprev^(b d) are entries of the 64th-root table in the constant bank (512 = 16 x 16 x 2: Mprev = 32,
+                // b = t & 1): no product tree, no shared-memory read - this pass is FP64-bound at 512 points
+#pragma unroll
+                for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmul(v[u * St::R + d], c64((64 / St::Mprev) * b * d));
+            } else {
+                mul_twiddle_powers<St::R, false>(v + u * St::R, tw.tw1[St::M + b]);
+            }
 #endif
         }
     }
@@ -417,7 +424,12 @@ __device__ __forceinline__ void inv_stage(cd* v, int t, const TwState<N>& tw) {
 #pragma unroll
             for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmulc(v[u * St::R + d], tw.tw1[d * St::M + b]);
 #else
-            mul_twiddle_powers<St::R, true>(v + u * St::R, tw.tw1[St::M + b]);
+            if constexpr (false && St::M == 2) {   // measured slower (divergent constant-bank reads): 512^3 apply 18.7 -> 19.4 ms; the product tree stays
+#pragma unroll
+                for (int d = 1; d < St::R; ++d) v[u * St::R + d] = cmulc(v[u * St::R + d], c64((64 / St::Mprev) * b * d));
+            } else {
+                mul_twiddle_powers<St::R, true>(v + u * St::R, tw.tw1[St::M + b]);
+            }
 #endif
         }
         dftR<+1, St::R>(v + u * St::R);

@@ -57,7 +57,11 @@ def main():
     k = 2 * np.pi / (10 * h)
     x = -0.5 + h * np.arange(n)
     Mo = O.buildFastConvolution3D(x, x, x, h, k, O.nu_gaussian_3d)
+    # at this size (2 MB per peer) the automatic route is NCCL; the copy-engine route (IPC pushes + flags) is forced for the
+    # operator the rest of the worker uses, and both are compared bit for bit below
+    os.environ["LS_OP3D_XCHG"] = "ce"
     M = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid)
+    del os.environ["LS_OP3D_XCHG"]
     rng = np.random.default_rng(1234)
     b = rng.standard_normal(n ** 3) + 1j * rng.standard_normal(n ** 3)
     y_ref = Mo * b
@@ -78,19 +82,20 @@ def main():
     M4.destroy()
     # the default transposes run on the copy engines (pushes into IPC-mapped peer buffers); the NCCL all-to-all gives the same bits
     assert M.info() == (2, 1, "copy-engine"), M.info()
-    os.environ["LS_OP3D_XCHG"] = "nccl"
     uidn = lsd.broadcast_unique_id(rank)
     Mn = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uidn)
-    del os.environ["LS_OP3D_XCHG"]
-    assert Mn.info()[2] == "nccl"
+    assert Mn.info()[2] == "nccl"                    # automatic choice below LS_OP3D_CE_MIN_MB per peer
     yn = Mn * np.ascontiguousarray(b[a:b_])
     assert np.array_equal(yn, y)
     Mn.destroy()
     # large slabs pipeline their transposes over x-slot chunks (on a second stream); forced here: same bits
     os.environ["LS_OP3D_CHUNKS"] = "4"
+    os.environ["LS_OP3D_XCHG"] = "ce"               # chunked copy-engine pushes with flag completion: the 512^3 configuration's route
     uid1 = lsd.broadcast_unique_id(rank)
     M1 = lsd.FastM3DSharded(Mo.nu[a:b_], n, n, l, k, 1.8 * n * h, 4.0 * n * h, rank, world, uid1)
     del os.environ["LS_OP3D_CHUNKS"]
+    del os.environ["LS_OP3D_XCHG"]
+    assert M1.info() == (2, 4, "copy-engine")
     y1 = M1 * np.ascontiguousarray(b[a:b_])
     assert np.array_equal(y1, y)
     for _ in range(3):                               # back-to-back applies reuse the exchange buffers and events

@@ -36,3 +36,15 @@ def test_nu_plasma_2d_matches_the_oracle():
     a, b = nu_plasma_2d(X, Y), O.nu_plasma_2d(X, Y)
     assert np.abs(a - b).max() <= 1e-15 * np.abs(b).max()
     assert (a == 0).sum() > 100 and np.unique(a).size > 100
+
+
+def test_nu_layered_3d_slab_is_a_slab_of_the_full_grid():
+    from fast_solver_lippmann_schwinger_b200.problems import nu_layered_3d_slab
+    n = 16
+    full = nu_layered_3d_slab(n, 0, n)
+    assert full.shape == (n ** 3,) and set(np.unique(full)) == {0.0, 0.02, 0.05, 0.08, 0.10}
+    parts = [nu_layered_3d_slab(n, p0, p0 + 4) for p0 in range(0, n, 4)]
+    assert np.array_equal(np.concatenate(parts), full)
+    cube = full.reshape(n, n, n, order="F")
+    assert np.all(cube[0] == 0) and np.all(cube[:, 0] == 0) and np.all(cube[:, :, 0] == 0)       # zero outside the box
+    assert all(np.unique(cube[1:, 1:, p]).size == 1 for p in range(1, n))                          # piecewise constant in z
