@@ -527,6 +527,7 @@ def bench_gmres_precond(args, ls, peak):
            "gpu_loop_s": dt - hist.msp_host_seconds, "msp_solve_s": (hist.mvps) * msp_ms * 1e-3, "msp_solve_ms_each": msp_ms,
            "pcie_s": 0.0, "msp_host_s": hist.msp_host_seconds,
            "msp_factor": {"bytes": F.factor_bytes, "depth": F.depth, "seconds": F.factor_seconds, "call_seconds": t_fac,
+                          "plan": F.plan().splitlines()[0],
                           "solve_GBs": F.factor_bytes / msp_ms / 1e6, "solve_hbm_frac": F.factor_bytes / msp_ms / 1e6 / peak},
            "setup_s": {"operator": t_op, "sparsifier_matrices": t_sp, "msp_factorisation": t_fac},
            "note": "Pl = Msp^-1 As entirely on the GPU (ls_gmres_msp): no host work and no PCIe traffic per iteration; "

@@ -20,6 +20,7 @@
 // numbers for a square grid: 13 GB at 2048^2, read once per solve).  Reductions run in a fixed order: deterministic.
 #include "ls_common.cuh"
 #include "spmv.cuh"
+#include "msp_gemv.cuh"
 #include <cublas_v2.h>
 #include <algorithm>
 #include <chrono>
@@ -45,6 +46,11 @@ struct Level {                            // all 2^d nodes of one depth
     cd* d_g = nullptr;                    // [count][Sp+Bp]   assembled right-hand side
     cd* d_z = nullptr;                    // [count][Sp]
     cd* d_t = nullptr;                    // [count][Bp]      update vector passed to the parent
+    // solver 2: blocks packed tightly with the nodes' actual sizes (msp_gemv.cuh); d_Sinv / d_FBS / d_Y then hold
+    // node t's ns x ns, nb x ns and ns x nb blocks at offS[t], offB[t], offB[t]
+    int* d_ns = nullptr; int* d_nb = nullptr;
+    long* d_offS = nullptr; long* d_offB = nullptr;
+    lsmsp::Choice ch_sinv{2, 2, 0}, ch_fbs{2, 2, 0}, ch_y{2, 2, 1};   // kernel geometry of the three sweeps of this depth
 };
 
 struct Msp : MspBase {
@@ -54,8 +60,17 @@ struct Msp : MspBase {
     size_t factor_bytes = 0;
     double factor_seconds = 0.0;
     cublasHandle_t cublas = nullptr;
+    // solver 1: uniform (identity-padded) batches, k_msp_gather + k_msp_gemv (round-2 first version, kept selectable);
+    // solver 2 (default): tightly packed blocks, gather fused into the sweeps, per-launch geometry (msp_gemv.cuh).
+    // LS_MSP_SOLVER / LS_MSP_FUSE / LS_MSP_TUNE are read when the handle is created.
+    int solver = 2;
+    bool fuse = true, tune = true;
+    double tune_seconds = 0.0;
     int solve_dev(const cd* rhs, cd* out, cudaStream_t s) override;
     int solve_launch(const cd* rhs, cd* out, cudaStream_t s);
+    int solve_launch2(const cd* rhs, cd* out, cudaStream_t s);
+    int sweep_args(int d, int which, const cd* rhs, cd* out, lsmsp::Gemv2& a) const;
+    int tune_sweeps();
     // the 4 x (depth + 1) dependent launches of one solve, captured once per (rhs, out) pair and replayed as a CUDA graph
     // (GMRES calls the solve with at most restart + 2 different pairs): removes the launch gaps between the small kernels
     struct Captured { const cd* rhs; cd* out; cudaGraphExec_t exec; };
@@ -182,6 +197,52 @@ int launch_gemv(const GemvArgs& a, cudaStream_t s) {
         default: k_msp_gemv<32, UNR><<<blocks, 256, 0, s>>>(a, rblocks, (unsigned)ngroups); break;
     }
     return LS_OK;
+}
+
+// ---- solver 2: ragged batches, launch geometry per sweep (msp_gemv.cuh) --------------------------------------------
+typedef void (*gemv2_fn)(const lsmsp::Gemv2, const lsmsp::Geo);
+#define LS_G2_U(L, U) { lsmsp::k_msp_gemv2<L, U, false>, lsmsp::k_msp_gemv2<L, U, true> }
+#define LS_G2_L(L) { LS_G2_U(L, 1), LS_G2_U(L, 2), LS_G2_U(L, 4), LS_G2_U(L, 8) }
+const gemv2_fn gemv2_table[6][4][2] = { LS_G2_L(1), LS_G2_L(2), LS_G2_L(4), LS_G2_L(8), LS_G2_L(16), LS_G2_L(32) };
+constexpr size_t GEMV2_SMEM_MAX = 48 * 1024;      // the default dynamic shared-memory limit: no per-device opt-in needed
+
+inline bool gemv2_valid(const lsmsp::Gemv2& a, const lsmsp::Choice& ch) {
+    if (ch.lanes_log2 < 0 || ch.lanes_log2 > 5 || ch.unr_log2 < 0 || ch.unr_log2 > 3) return false;
+    return lsmsp::launch_geo(a.rows_p, a.cols_p, a.nodes, ch).smem <= GEMV2_SMEM_MAX;
+}
+
+int launch_gemv2(const lsmsp::Gemv2& a, lsmsp::Choice ch, cudaStream_t s) {
+    if (a.nodes <= 0 || a.rows_p <= 0) return LS_OK;
+    if (!gemv2_valid(a, ch)) ch.xs = 0;                // X too long for the staging buffer: every group fetches it itself
+    const lsmsp::LaunchGeo L = lsmsp::launch_geo(a.rows_p, a.cols_p, a.nodes, ch);
+    gemv2_table[ch.lanes_log2][ch.unr_log2][ch.xs ? 1 : 0]<<<L.grid, 256, L.smem, s>>>(a, L.g);
+    return LS_OK;
+}
+
+// column-major factor blocks of the uniform batch -> tightly packed row-major blocks of the nodes' actual sizes
+__global__ void k_msp_pack_tight(const cd* __restrict__ Cinv, const cd* __restrict__ Ytmp, const cd* __restrict__ F, int Sp, int Bp,
+                                 long count, const int* __restrict__ ns, const int* __restrict__ nb,
+                                 const long* __restrict__ offS, const long* __restrict__ offB, cd* Sinv, cd* FBS, cd* Y) {
+    const int Fp = Sp + Bp;
+    const long nS = (long)Sp * Sp, nB = (long)Sp * Bp;
+    const long per = nS + 2 * nB;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count * per; e += (long)gridDim.x * blockDim.x) {
+        const long t = e / per;
+        long r = e % per;
+        const int s_t = ns[t], b_t = nb[t];
+        if (r < nS) {
+            const int i = (int)(r / Sp), j = (int)(r % Sp);
+            if (i < s_t && j < s_t) Sinv[offS[t] + (long)i * s_t + j] = Cinv[t * nS + i + (long)j * Sp];
+        } else if (r < nS + nB) {
+            r -= nS;
+            const int b = (int)(r / Sp), sidx = (int)(r % Sp);
+            if (b < b_t && sidx < s_t) FBS[offB[t] + (long)b * s_t + sidx] = F[t * (long)Fp * Fp + (Sp + b) + (long)sidx * Fp];
+        } else {
+            r -= nS + nB;
+            const int sidx = (int)(r / Bp), b = (int)(r % Bp);
+            if (b < b_t && sidx < s_t) Y[offB[t] + (long)sidx * b_t + b] = Ytmp[t * nB + sidx + (long)b * Sp];
+        }
+    }
 }
 
 // ---- factorisation kernels ------------------------------------------------------------------------------------
@@ -459,13 +520,32 @@ int msp_factor(Msp* M, int n, int m, const int64_t* colptr, const int64_t* rowva
         if ((rc = M->dupload((void**)&L.d_Sidx, hSidx[d].data(), cnt * Sp * sizeof(int)))) return rc;
         if ((rc = M->dupload((void**)&L.d_Bidx, hBidx[d].data(), cnt * std::max<size_t>(Bp, 1) * sizeof(int)))) return rc;
         if (d < D && (rc = M->dupload((void**)&L.d_pmap, hpmap[d].data(), cnt * 2 * Fp * sizeof(int)))) return rc;
-        if ((rc = M->dmalloc((void**)&L.d_Sinv, cnt * Sp * Sp * sizeof(cd)))) return rc;
-        if ((rc = M->dmalloc((void**)&L.d_FBS, std::max<size_t>(cnt * Sp * Bp, 1) * sizeof(cd)))) return rc;
-        if ((rc = M->dmalloc((void**)&L.d_Y, std::max<size_t>(cnt * Sp * Bp, 1) * sizeof(cd)))) return rc;
+        size_t totS = cnt * Sp * Sp, totB = cnt * Sp * Bp;
+        if (M->solver == 2) {
+            // actual sizes (the valid entries lead every node's list) and the offsets of the tightly packed blocks
+            std::vector<int> hns(cnt), hnb(cnt);
+            std::vector<long> hoffS(cnt), hoffB(cnt);
+            totS = 0; totB = 0;
+            for (size_t t = 0; t < cnt; ++t) {
+                int s_t = 0, b_t = 0;
+                while (s_t < (int)Sp && hSidx[d][t * Sp + s_t] >= 0) ++s_t;
+                while (b_t < (int)Bp && hBidx[d][t * Bp + b_t] >= 0) ++b_t;
+                hns[t] = s_t; hnb[t] = b_t;
+                hoffS[t] = (long)totS; hoffB[t] = (long)totB;
+                totS += (size_t)s_t * s_t; totB += (size_t)s_t * b_t;
+            }
+            if ((rc = M->dupload((void**)&L.d_ns, hns.data(), cnt * sizeof(int)))) return rc;
+            if ((rc = M->dupload((void**)&L.d_nb, hnb.data(), cnt * sizeof(int)))) return rc;
+            if ((rc = M->dupload((void**)&L.d_offS, hoffS.data(), cnt * sizeof(long)))) return rc;
+            if ((rc = M->dupload((void**)&L.d_offB, hoffB.data(), cnt * sizeof(long)))) return rc;
+        }
+        if ((rc = M->dmalloc((void**)&L.d_Sinv, std::max<size_t>(totS, 1) * sizeof(cd)))) return rc;
+        if ((rc = M->dmalloc((void**)&L.d_FBS, std::max<size_t>(totB, 1) * sizeof(cd)))) return rc;
+        if ((rc = M->dmalloc((void**)&L.d_Y, std::max<size_t>(totB, 1) * sizeof(cd)))) return rc;
         if ((rc = M->dmalloc((void**)&L.d_g, cnt * Fp * sizeof(cd)))) return rc;
         if ((rc = M->dmalloc((void**)&L.d_z, cnt * Sp * sizeof(cd)))) return rc;
         if ((rc = M->dmalloc((void**)&L.d_t, std::max<size_t>(cnt * Bp, 1) * sizeof(cd)))) return rc;
-        fbytes += cnt * (Sp * Sp + 2 * Sp * Bp) * sizeof(cd);
+        fbytes += (totS + 2 * totB) * sizeof(cd);
     }
     M->factor_bytes = fbytes;
 
@@ -536,7 +616,11 @@ int msp_factor(Msp* M, int n, int m, const int64_t* colptr, const int64_t* rowva
                                                     reinterpret_cast<cuDoubleComplex*>(Ytmp), (int)Sp, Sp * Bp, &one,
                                                     reinterpret_cast<cuDoubleComplex*>(F + Sp + Sp * Fp), (int)Fp, Fp * Fp, (int)cnt));
         }
-        k_msp_pack<<<grid_for(cnt * (Sp * Sp + 2 * Sp * Bp)), 256, 0, s>>>(Cinv, Ytmp, F, (int)Sp, (int)Bp, cnt, L.d_Sinv, L.d_FBS, L.d_Y);
+        if (M->solver == 2)
+            k_msp_pack_tight<<<grid_for(cnt * (Sp * Sp + 2 * Sp * Bp)), 256, 0, s>>>(Cinv, Ytmp, F, (int)Sp, (int)Bp, cnt, L.d_ns, L.d_nb,
+                                                                                    L.d_offS, L.d_offB, L.d_Sinv, L.d_FBS, L.d_Y);
+        else
+            k_msp_pack<<<grid_for(cnt * (Sp * Sp + 2 * Sp * Bp)), 256, 0, s>>>(Cinv, Ytmp, F, (int)Sp, (int)Bp, cnt, L.d_Sinv, L.d_FBS, L.d_Y);
         LS_CUDA_TRY(cudaStreamSynchronize(s));
         LS_CUDA_TRY(cudaGetLastError());
         M->dfree(Cinv); M->dfree(Ytmp); M->dfree(pA); M->dfree(pC); M->dfree(piv); M->dfree(info);
@@ -552,33 +636,34 @@ int msp_factor(Msp* M, int n, int m, const int64_t* colptr, const int64_t* rowva
 }  // namespace
 
 int Msp::solve_dev(const cd* rhs, cd* out, cudaStream_t s) {
+    auto launch = [this](const cd* r, cd* o, cudaStream_t st) { return solver == 2 ? solve_launch2(r, o, st) : solve_launch(r, o, st); };
     if (use_graph < 0) { const char* e = getenv("LS_MSP_GRAPH"); use_graph = e ? atoi(e) : 1; }
-    if (!use_graph) return solve_launch(rhs, out, s);
+    if (!use_graph) return launch(rhs, out, s);
     for (auto& g : graphs)
         if (g.rhs == rhs && g.out == out) {
             LS_CUDA_TRY(cudaGraphLaunch(g.exec, s));
             launches += launches_per_solve;
             return LS_OK;
         }
-    if (graphs.size() >= 64) return solve_launch(rhs, out, s);
+    if (graphs.size() >= 64) return launch(rhs, out, s);
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
         use_graph = 0;
-        return solve_launch(rhs, out, s);
+        return launch(rhs, out, s);
     }
-    const int rc = solve_launch(rhs, out, s);
+    const int rc = launch(rhs, out, s);
     const cudaError_t ce = cudaStreamEndCapture(s, &graph);
     if (rc != LS_OK || ce != cudaSuccess || graph == nullptr) {
         cudaGetLastError();
         if (graph) cudaGraphDestroy(graph);
         use_graph = 0;
-        return solve_launch(rhs, out, s);
+        return launch(rhs, out, s);
     }
     cudaGraphExec_t exec = nullptr;
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) { cudaGetLastError(); use_graph = 0; return solve_launch(rhs, out, s); }
+    if (ie != cudaSuccess) { cudaGetLastError(); use_graph = 0; return launch(rhs, out, s); }
     graphs.push_back(Captured{rhs, out, exec});
     LS_CUDA_TRY(cudaGraphLaunch(exec, s));
     return LS_OK;
@@ -623,6 +708,138 @@ int Msp::solve_launch(const cd* rhs, cd* out, cudaStream_t s) {
     return LS_OK;
 }
 
+// ---- solver 2 ----------------------------------------------------------------------------------------------------
+// arguments of sweep `which` of depth d:  0  z = Sinv g_S   1  t = g_B - F_BS z   2  u_S = z - Y u_B
+int Msp::sweep_args(int d, int which, const cd* rhs, cd* out, lsmsp::Gemv2& a) const {
+    const int D = (int)lev.size() - 1;
+    const Level& L = lev[d];
+    const Level* Lc = d < D ? &lev[d + 1] : nullptr;
+    const int Fp = L.Sp + L.Bp;
+    a = lsmsp::Gemv2{};
+    a.nodes = L.count;
+    a.pmap = Lc ? L.d_pmap : nullptr; a.tchild = Lc ? Lc->d_t : nullptr; a.Fp = Fp; a.Bpc = Lc ? Lc->Bp : 0;
+    if (which == 0) {
+        a.M = L.d_Sinv; a.moff = L.d_offS; a.nrows = L.d_ns; a.ncols = L.d_ns; a.rows_p = L.Sp; a.cols_p = L.Sp;
+        if (fuse) { a.xmode = 2; a.f = rhs; a.sidx = L.d_Sidx; }
+        else { a.xmode = 0; a.x = L.d_g; a.xstride = Fp; }
+        a.ymode = 0; a.sign = 1.0;
+        a.out = L.d_z; a.ostride = L.Sp;
+    } else if (which == 1) {
+        a.M = L.d_FBS; a.moff = L.d_offB; a.nrows = L.d_nb; a.ncols = L.d_ns; a.rows_p = L.Bp; a.cols_p = L.Sp;
+        a.xmode = 0; a.x = L.d_z; a.xstride = L.Sp;
+        if (fuse) a.ymode = 2;
+        else { a.ymode = 1; a.y0 = L.d_g + L.Sp; a.y0stride = Fp; }
+        a.sign = -1.0;
+        a.out = L.d_t; a.ostride = L.Bp;
+    } else {
+        a.M = L.d_Y; a.moff = L.d_offB; a.nrows = L.d_ns; a.ncols = L.d_nb; a.rows_p = L.Sp; a.cols_p = L.Bp;
+        a.xmode = 1; a.xidx = L.d_Bidx; a.xg = out;
+        a.ymode = 1; a.y0 = L.d_z; a.y0stride = L.Sp; a.sign = -1.0;
+        a.oidx = L.d_Sidx; a.og = out;
+    }
+    return LS_OK;
+}
+
+int Msp::solve_launch2(const cd* rhs, cd* out, cudaStream_t s) {
+    const int D = (int)lev.size() - 1;
+    lsmsp::Gemv2 a;
+    for (int d = D; d >= 0; --d) {                      // upward: leaves -> root
+        Level& L = lev[d];
+        if (!fuse) {
+            const int Fp = L.Sp + L.Bp;
+            const long total = (long)L.count * Fp;
+            const Level* Lc = d < D ? &lev[d + 1] : nullptr;
+            k_msp_gather<<<grid_for(total), 256, 0, s>>>(rhs, L.d_Sidx, Lc ? L.d_pmap : nullptr, Lc ? Lc->d_t : nullptr, L.Sp, Fp,
+                                                         Lc ? Lc->Bp : 0, total, L.d_g);
+        }
+        sweep_args(d, 0, rhs, out, a);
+        launch_gemv2(a, L.ch_sinv, s);
+        if (L.Bp > 0) {
+            sweep_args(d, 1, rhs, out, a);
+            launch_gemv2(a, L.ch_fbs, s);
+        }
+    }
+    for (int d = 0; d <= D; ++d) {                      // downward: root -> leaves, u_S written straight into `out`
+        sweep_args(d, 2, rhs, out, a);
+        launch_gemv2(a, lev[d].ch_y, s);
+    }
+    launches += launches_per_solve;
+    LS_CUDA_TRY(cudaGetLastError());
+    return LS_OK;
+}
+
+// Times every admissible (LANES, UNR, XS) of every sweep once, on the blocks just factorised (cold L2: a buffer larger
+// than the L2 is cleared before each timed launch, as in a solve every block arrives from HBM), and keeps the fastest.
+// The sweeps are idempotent on fixed inputs, so the candidates simply run one after the other in solve order.
+int Msp::tune_sweeps() {
+    const auto t_start = std::chrono::steady_clock::now();
+    const int D = (int)lev.size() - 1;
+    cudaStream_t s = stream;
+    cd *f = nullptr, *u = nullptr;
+    void* flush = nullptr;
+    int rc;
+    const size_t vb = (size_t)n * sizeof(cd);
+    const size_t flush_bytes = factor_bytes > ((size_t)64 << 20) ? ((size_t)192 << 20) : 0;    // small factors live in the L2 anyway
+    if ((rc = dmalloc((void**)&f, vb))) return rc;
+    if ((rc = dmalloc((void**)&u, vb))) return rc;
+    if (flush_bytes && (rc = dmalloc(&flush, flush_bytes))) return rc;
+    LS_CUDA_TRY(cudaMemsetAsync(f, 0, vb, s));
+    LS_CUDA_TRY(cudaMemsetAsync(u, 0, vb, s));
+    for (Level& L : lev) {
+        LS_CUDA_TRY(cudaMemsetAsync(L.d_g, 0, (size_t)L.count * (L.Sp + L.Bp) * sizeof(cd), s));
+        LS_CUDA_TRY(cudaMemsetAsync(L.d_z, 0, (size_t)L.count * L.Sp * sizeof(cd), s));
+        LS_CUDA_TRY(cudaMemsetAsync(L.d_t, 0, std::max<size_t>((size_t)L.count * L.Bp, 1) * sizeof(cd), s));
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    LS_CUDA_TRY(cudaEventCreate(&e0));
+    LS_CUDA_TRY(cudaEventCreate(&e1));
+    auto tune_one = [&](int d, int which, lsmsp::Choice& best) -> int {
+        lsmsp::Gemv2 a;
+        sweep_args(d, which, f, u, a);
+        if (a.nodes <= 0 || a.rows_p <= 0) return LS_OK;
+        const lsmsp::Choice def = lsmsp::default_choice(a.cols_p, a.xmode);
+        float best_ms = 1e30f;
+        lsmsp::Choice pick = def;
+        if (!gemv2_valid(a, pick)) pick.xs = 0;
+        for (int ll = std::max(0, def.lanes_log2 - 2); ll <= std::min(5, def.lanes_log2 + 1); ++ll)
+            for (int ul = 0; ul <= 3; ++ul)
+                for (int xs = 0; xs <= 1; ++xs) {
+                    const lsmsp::Choice ch{ll, ul, xs};
+                    if (!gemv2_valid(a, ch)) continue;
+                    if ((1 << ul) > std::max(a.rows_p, 1) * 2) continue;          // more rows per group than the block has
+                    launch_gemv2(a, ch, s);                                        // warm-up: instruction cache, first touch
+                    float ms = 1e30f;
+                    for (int rep = 0; rep < 2; ++rep) {
+                        if (flush) LS_CUDA_TRY(cudaMemsetAsync(flush, 0, flush_bytes, s));
+                        LS_CUDA_TRY(cudaEventRecord(e0, s));
+                        launch_gemv2(a, ch, s);
+                        LS_CUDA_TRY(cudaEventRecord(e1, s));
+                        LS_CUDA_TRY(cudaEventSynchronize(e1));
+                        float t = 0.f;
+                        LS_CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+                        ms = std::min(ms, t);
+                    }
+                    if (ms < best_ms) { best_ms = ms; pick = ch; }
+                }
+        best = pick;
+        return LS_OK;
+    };
+    for (int d = D; d >= 0 && rc == LS_OK; --d) {
+        rc = tune_one(d, 0, lev[d].ch_sinv);
+        if (rc == LS_OK && lev[d].Bp > 0) rc = tune_one(d, 1, lev[d].ch_fbs);
+    }
+    for (int d = 0; d <= D && rc == LS_OK; ++d) rc = tune_one(d, 2, lev[d].ch_y);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc == LS_OK) {
+        cudaError_t ce = cudaStreamSynchronize(s);
+        if (ce == cudaSuccess) ce = cudaGetLastError();
+        if (ce != cudaSuccess) { set_error("ls_msp_factor: tuning the solve sweeps failed: %s", cudaGetErrorString(ce)); rc = LS_ERR_CUDA; }
+    }
+    dfree(f); dfree(u); dfree(flush);
+    tune_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    return rc;
+}
+
 extern "C" {
 
 int ls_msp_factor(ls_handle* out, int64_t n, int64_t m, const int64_t* colptr, const int64_t* rowval, const ls_cdouble* nzval) {
@@ -636,8 +853,22 @@ int ls_msp_factor(ls_handle* out, int64_t n, int64_t m, const int64_t* colptr, c
     int rc = M->init_base(KIND_MSP);
     if (rc) { delete M; return rc; }
     M->n = n * m; M->gn = n; M->gm = m;
+    if (const char* e = getenv("LS_MSP_SOLVER")) M->solver = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = getenv("LS_MSP_FUSE")) M->fuse = atoi(e) != 0;
+    if (const char* e = getenv("LS_MSP_TUNE")) M->tune = atoi(e) != 0;
     rc = msp_factor(M, (int)n, (int)m, colptr, rowval, reinterpret_cast<const cd*>(nzval), leaf);
     if (rc) { delete M; return rc; }
+    if (M->solver == 2) {
+        for (Level& L : M->lev) {
+            L.ch_sinv = lsmsp::default_choice(L.Sp, M->fuse ? 2 : 0);
+            L.ch_fbs = lsmsp::default_choice(L.Sp, 0);
+            L.ch_y = lsmsp::default_choice(L.Bp, 1);
+        }
+        M->launches_per_solve = 0;
+        for (const Level& L : M->lev) M->launches_per_solve += (M->fuse ? 0 : 1) + 2 + (L.Bp > 0 ? 1 : 0);
+        if (M->tune) rc = M->tune_sweeps();
+        if (rc) { delete M; return rc; }
+    }
     *out = reinterpret_cast<ls_handle>(M);
     return LS_OK;
 }
@@ -671,6 +902,35 @@ int ls_msp_info(ls_handle h, int64_t* factor_bytes, int* depth, double* factor_s
     if (factor_bytes) *factor_bytes = (int64_t)M->factor_bytes;
     if (depth) *depth = (int)M->lev.size() - 1;
     if (factor_seconds) *factor_seconds = M->factor_seconds;
+    return LS_OK;
+}
+
+int ls_msp_plan(ls_handle h, char* buf, int64_t cap) {
+    LS_REQUIRE(h && buf && cap > 0, LS_ERR_INVALID, "ls_msp_plan: null argument");
+    Msp* M = reinterpret_cast<Msp*>(h);
+    LS_REQUIRE(M->kind == KIND_MSP, LS_ERR_INVALID, "ls_msp_plan: not an Msp factorisation handle");
+    std::string out;
+    char line[256];
+    snprintf(line, sizeof line, "solver %d fuse %d tune %d tune_seconds %.3f launches_per_solve %d factor_bytes %zu\n", M->solver,
+             M->fuse ? 1 : 0, M->tune ? 1 : 0, M->tune_seconds, M->launches_per_solve, M->factor_bytes);
+    out += line;
+    for (size_t d = 0; d < M->lev.size(); ++d) {
+        const Level& L = M->lev[d];
+        snprintf(line, sizeof line, "depth %zu nodes %d Sp %d Bp %d", d, L.count, L.Sp, L.Bp);
+        out += line;
+        if (M->solver == 2) {
+            const lsmsp::Choice* ch[3] = {&L.ch_sinv, &L.ch_fbs, &L.ch_y};
+            const char* nm[3] = {"sinv", "fbs", "y"};
+            for (int w = 0; w < 3; ++w) {
+                snprintf(line, sizeof line, " %s L%d U%d X%d", nm[w], 1 << ch[w]->lanes_log2, 1 << ch[w]->unr_log2, ch[w]->xs);
+                out += line;
+            }
+        }
+        out += "\n";
+    }
+    const size_t ncopy = std::min<size_t>(out.size(), (size_t)cap - 1);
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
     return LS_OK;
 }
 

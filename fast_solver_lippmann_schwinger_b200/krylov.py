@@ -111,6 +111,13 @@ class GPUMspFactorization(_Handle):
         check(lib().ls_msp_info(self.handle, C.byref(fb), C.byref(dep), C.byref(sec)))
         self.factor_bytes, self.depth, self.factor_seconds = int(fb.value), int(dep.value), float(sec.value)
 
+    def plan(self):
+        """Text description of the solve plan (ls_msp_plan): solver version and, per dissection depth, the block sizes and
+        the kernel geometry of the three sweeps."""
+        buf = C.create_string_buffer(16384)
+        check(lib().ls_msp_plan(self.handle, buf, len(buf)))
+        return buf.value.decode()
+
     def solve(self, b, out=None):
         if isinstance(b, DeviceBuffer):
             out = b if out is None else out

@@ -191,6 +191,10 @@ int ls_msp_factor(ls_handle* out, int64_t n, int64_t m, const int64_t* colptr, c
 /* x <- Msp^-1 rhs (x may alias rhs); host or device pointers per memloc */
 int ls_msp_solve(ls_handle msp, const ls_cdouble* rhs, ls_cdouble* x, int memloc);
 int ls_msp_info(ls_handle msp, int64_t* factor_bytes, int* depth, double* factor_seconds);
+/* one line per dissection depth: node count, padded block sizes and the kernel geometry (lanes per row group, rows per
+ * group, X staged in shared memory) chosen for its three sweeps; first line: solver version, fusion, tuning time.
+ * Writes at most `cap` bytes including the terminator into `buf` (diagnostics for bench / profiles).               */
+int ls_msp_plan(ls_handle msp, char* buf, int64_t cap);
 /* ls_gmres with ldiv!(Pl, v) = Msp^-1 (As v) entirely on the device (`msp` from ls_msp_factor, `As` nullable) */
 int ls_gmres_msp(ls_handle krylov, ls_handle op, ls_handle As, ls_handle msp,
                  const ls_cdouble* b, ls_cdouble* x, int restart, int64_t maxiter, double reltol,

@@ -213,6 +213,11 @@ function msp_info(F::GPUMspFactorization)
     check(ccall((:ls_msp_info, libls), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Cint}, Ref{Float64}), F.h.ptr, fb, dep, sec))
     return (factor_bytes=fb[], depth=dep[], factor_seconds=sec[])
 end
+function msp_plan(F::GPUMspFactorization)
+    buf = Vector{UInt8}(undef, 8192)
+    check(ccall((:ls_msp_plan, libls), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), F.h.ptr, buf, length(buf)))
+    return unsafe_string(pointer(buf))
+end
 
 struct GPUSparsifyingPreconditioner      # preconditioner.jl:27-58
     Msp::SparseMatrixCSC{ComplexF64,Int64}

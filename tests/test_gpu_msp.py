@@ -58,6 +58,61 @@ def test_msp_solve_matches_superlu(n, m):
     F.destroy()
 
 
+# solver 1 = the uniform-batch kernels of the first version; solver 2 = tightly packed ragged batches (msp_gemv.cuh) with
+# the gather kernel kept (fuse 0) or fused into the sweeps, launch geometry by the fixed rule (tune 0) or timed (tune 1)
+MSP_CONFIGS = [("1", "0", "0"), ("2", "0", "0"), ("2", "1", "0"), ("2", "0", "1"), ("2", "1", "1")]
+
+
+@pytest.mark.parametrize("solver,fuse,tune", MSP_CONFIGS)
+def test_msp_solver_variants_agree(solver, fuse, tune, monkeypatch):
+    """Every solver configuration against SuperLU on ragged dissections (odd and non-square grids, grids smaller than a
+    leaf), in place, with the CUDA-graph replay and without it."""
+    import fast_solver_lippmann_schwinger_b200 as ls
+    monkeypatch.setenv("LS_MSP_SOLVER", solver)
+    monkeypatch.setenv("LS_MSP_FUSE", fuse)
+    monkeypatch.setenv("LS_MSP_TUNE", tune)
+    for (n, m), graph in (((1, 1), "1"), ((3, 2), "1"), ((9, 4), "0"), ((17, 33), "1"), ((40, 25), "0"), ((130, 257), "1"), ((201, 201), "1")):
+        monkeypatch.setenv("LS_MSP_GRAPH", graph)
+        A = stencil9(n, m, seed=7 * n + m)
+        rng = np.random.default_rng(n + m)
+        b = rng.standard_normal(n * m) + 1j * rng.standard_normal(n * m)
+        x_ref = spla.splu(A).solve(b)
+        F = ls.GPUMspFactorization(A, n, m)
+        plan = F.plan()
+        assert plan.startswith("solver %s " % solver), plan.splitlines()[0]
+        if solver == "2":
+            assert ("fuse %s tune %s" % (fuse, tune)) in plan.splitlines()[0]
+        assert _rel(F.solve(b), x_ref) < 1e-10, (n, m, plan.splitlines()[0])
+        db, dx = ls.DeviceBuffer.from_host(b), ls.DeviceBuffer(b.nbytes)
+        for _ in range(3):                                  # the first call captures the graph, the next ones replay it
+            F.solve(db, dx)
+        F.sync()
+        assert _rel(dx.to_host(), x_ref) < 1e-10
+        F.solve(db)                                         # in place
+        F.sync()
+        assert _rel(db.to_host(), x_ref) < 1e-10
+        db.free(); dx.free()
+        F.destroy()
+
+
+def test_msp_tight_packing_drops_the_padding():
+    """Solver 2 stores the blocks with the nodes' actual sizes: fewer bytes than the identity-padded uniform batches."""
+    import os
+    import fast_solver_lippmann_schwinger_b200 as ls
+    n, m = 130, 257
+    A = stencil9(n, m, seed=5)
+    sizes = {}
+    for solver in ("1", "2"):
+        os.environ["LS_MSP_SOLVER"] = solver
+        try:
+            F = ls.GPUMspFactorization(A, n, m)
+        finally:
+            del os.environ["LS_MSP_SOLVER"]
+        sizes[solver] = F.factor_bytes
+        F.destroy()
+    assert 0 < sizes["2"] < sizes["1"]
+
+
 @pytest.mark.parametrize("leaf", ["3", "8"])
 def test_msp_leaf_size_does_not_change_the_answer(leaf, monkeypatch):
     import fast_solver_lippmann_schwinger_b200 as ls
