@@ -121,3 +121,59 @@ def test_product_sparsifier_against_dense_green_matrix():
         r = i + n * j
         assert np.array_equal(As.indices[As.indptr[r]:As.indptr[r + 1]] - r, As.indices[As.indptr[r0]:As.indptr[r0 + 1]] - r0)
         assert np.array_equal(As.data[As.indptr[r]:As.indptr[r + 1]], base)
+
+
+def test_product_sparsifier_3d_against_dense_green_matrix():
+    """3-D: every row of the product's buildSparseA3DConv against null vectors of the dense Green matrix, with the boundary
+    classes, their representatives and the stencils enumerated geometrically here (not through the class tables the
+    product and the oracle's sparsifier section share).  Representatives as in SparsifyingMatrix3D.jl:1166-1341:
+    coordinate 1 on a low face, n on a high face, round(n/2) otherwise (changeInd3D(...) calls at :1166, :1178, :1189,
+    :1199, :1208, :1217, :1225, :1233-1244, :1334-1341); stencil order = Ind_relative[...][:], x fastest."""
+    from fast_solver_lippmann_schwinger_b200 import sparsifier as S
+    n, m, l = 6, 6, 5                                        # FFTconvolution 3-D pads (ne, ne, le): n == m (Q3)
+    h = 1.0 / n
+    x = -0.5 + h * np.arange(n)
+    z = -0.5 + h * np.arange(l)
+    k = 2 * np.pi / (7.3 * h)
+    Mo = O.buildFastConvolution3D(x, x, z, h, k, O.nu_gaussian_3d)
+    N = n * m * l
+    G = np.empty((N, N), complex)                            # dense matrix of the convolution: column c = apply(e_c)
+    e = np.zeros(N, complex)
+    for c in range(N):
+        e[c] = 1.0
+        G[:, c] = O.FFTconvolution3D(Mo, e)
+        e[c] = 0.0
+    X, Y, Z = O.grid3d(x, x, z)
+    As = S.buildSparseA3DConv(k, X, Y, Z, object(), n, m, l, apply=lambda M, v: G @ v).tocsr()
+
+    def rnd_half(v):                                         # Julia's round(Integer, v/2): ties to even
+        return int(np.round(v / 2))
+
+    def rep_coord(c, size):                                  # 1-based coordinate of the class representative along one axis
+        return 1 if c == 1 else (size if c == size else rnd_half(size))
+
+    def neighbours(i, j, p):                                 # 1-based coordinates -> 0-based linear indices, x fastest
+        return [(ii - 1) + n * (jj - 1) + n * m * (pp - 1)
+                for pp in (p - 1, p, p + 1) for jj in (j - 1, j, j + 1) for ii in (i - 1, i, i + 1)
+                if 1 <= ii <= n and 1 <= jj <= m and 1 <= pp <= l]
+
+    cache = {}
+    sizes = set()
+    for p in range(1, l + 1):
+        for j in range(1, m + 1):
+            for i in range(1, n + 1):
+                rep = (rep_coord(i, n), rep_coord(j, m), rep_coord(p, l))
+                if rep not in cache:
+                    cache[rep] = _null_vector_dense(G, neighbours(*rep))
+                v = cache[rep]
+                st = neighbours(i, j, p)
+                assert len(st) == v.size
+                sizes.add(v.size)
+                r = (i - 1) + n * (j - 1) + n * m * (p - 1)
+                cols = As.indices[As.indptr[r]:As.indptr[r + 1]]
+                vals = As.data[As.indptr[r]:As.indptr[r + 1]]
+                assert sorted(cols) == st, (i, j, p)
+                a = vals[np.argsort(cols)]
+                ph = np.vdot(v, a) / abs(np.vdot(v, a))
+                assert np.abs(a - ph * v).max() < 1e-7 * np.abs(v).max(), (i, j, p)
+    assert len(cache) == 27 and sizes == {27, 18, 12, 8}
