@@ -142,16 +142,48 @@ def _last_left_singular_vector(GS):
 
 
 def _assemble(N, row_sets, Indices, Values):
-    rows, cols, vals = [], [], []
+    """createIndices (Functions.jl:7-29) over all boundary classes + sparse(row, col, val): every row of a class carries the
+    class's (relative column, value) list.  The classes partition the rows, so the matrix is written row by row (CSR) without
+    sorting 9 N / 27 N triplets, then converted to the CSC Julia holds."""
+    counts = np.zeros(N, dtype=np.int64)
+    sets = []
     for rset, ind, val in zip(row_sets, Indices, Values):
-        R, C, V = createIndices(rset, ind, val)
-        rows.append(R)
-        cols.append(C)
-        vals.append(V)
-    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows) - 1, np.concatenate(cols) - 1)), shape=(N, N)).tocsc()
-    A.sum_duplicates()
+        r = np.atleast_1d(np.asarray(rset, dtype=np.int64)).reshape(-1) - 1
+        ind = np.asarray(ind, dtype=np.int64).reshape(-1)
+        val = np.asarray(val, dtype=np.complex128).reshape(-1)
+        if ind.shape != val.shape:
+            raise AssertionError("length(col) == length(val)")
+        if r.size and (r.min() < 0 or r.max() >= N or r.min() + ind.min() < 0 or r.max() + ind.max() >= N):
+            raise IndexError("sparsifier stencil reaches outside the grid")
+        if np.any(counts[r] != 0):
+            raise AssertionError("boundary classes overlap")
+        counts[r] = ind.size
+        sets.append((r, ind, val))
+    indptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    indices = np.empty(int(indptr[-1]), dtype=np.int64)
+    data = np.empty(int(indptr[-1]), dtype=np.complex128)
+    for r, ind, val in sets:
+        for q in range(ind.size):                # one strided pass per stencil entry: no N x stencil temporaries
+            pos = indptr[r] + q
+            indices[pos] = r + ind[q]
+            data[pos] = val[q]
+    A = sp.csr_matrix((data, indices, indptr), shape=(N, N)).tocsc()
     A.sort_indices()
     return A
+
+
+def _same_pattern(A, B):
+    return A.shape == B.shape and A.nnz == B.nnz and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+
+
+def _system_matrix(As, AG, k, nu):
+    """Mapproxsp = As + k^2 AG diag(nu) (examples/example.jl:67).  As and AG share their pattern: one pass over the values."""
+    nu = np.asarray(nu, dtype=np.float64)
+    if As.format == "csc" and AG.format == "csc" and _same_pattern(As, AG):
+        col_nu = np.repeat(nu, np.diff(As.indptr))
+        return sp.csc_matrix((As.data + (k ** 2) * (AG.data * col_nu), As.indices.copy(), As.indptr.copy()), shape=As.shape)
+    return (As + k ** 2 * (AG @ sp.diags(nu))).tocsc()
 
 
 # ------------------------------------------------------------------------------------------- 3-D
@@ -240,7 +272,7 @@ def sparsifying_matrices_3d(k, X, Y, Z, fastconv, n, m, l, nu, apply=None):
     samples = _sample_classes_3d(fastconv, n, m, l, apply)
     As = buildSparseA3DConv(k, X, Y, Z, fastconv, n, m, l, apply, samples)
     AG = buildSparseAG3DConv(k, X, Y, Z, fastconv, n, m, l, apply, samples)
-    return As, (As + k ** 2 * (AG @ sp.diags(np.asarray(nu, dtype=np.float64)))).tocsc()
+    return As, _system_matrix(As, AG, k, nu)
 
 
 # ------------------------------------------------------------------------------------------- 2-D
@@ -352,4 +384,4 @@ def sparsifying_matrices_2d(k, X, Y, fastconv, n, m, nu, apply=None, strict=True
     samples = _sample_classes_2d(fastconv, n, m, apply, strict)
     As = buildSparseAConv(k, X, Y, fastconv, n, m, apply, strict, _cache=entriesSparseAConv(k, X, Y, fastconv, n, m, apply, strict, samples))
     AG = buildSparseAGConv(k, X, Y, fastconv, n, m, apply, strict, _samples=samples)
-    return As, (As + k ** 2 * (AG @ sp.diags(np.asarray(nu, dtype=np.float64)))).tocsc()
+    return As, _system_matrix(As, AG, k, nu)
