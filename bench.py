@@ -44,6 +44,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, and scipy's FFT (ducc) sizes its thread pool from it: the CPU
+# arm then ran on one core for N > 1 (0.90 -> 0.235 applies/s).  DUCC0_NUM_THREADS takes precedence; it has to be
+# in the environment before scipy.fft is first imported (the oracle is imported lazily, below).
+os.environ.setdefault("DUCC0_NUM_THREADS", str(os.cpu_count() or 1))
+
 METRIC = "ls_operator_applies_per_s_2d"
 UNIT = "applies/s"
 
