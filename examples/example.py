@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--n", type=int, default=201)
     ap.add_argument("--reltol", type=float, default=float(np.sqrt(np.finfo(float).eps)))
     ap.add_argument("--precond", default=None)
+    ap.add_argument("--msp", default="gpu", choices=["gpu", "host"],
+                    help="MspInv = lu(Msp) on the device (ls_msp_factor) or on the host (SuperLU through the solve callback)")
     args = ap.parse_args()
     n = args.n
     if n % 2 == 1:                       # example.jl: x = -a/2:h:a/2, k = 1/h
@@ -48,22 +50,24 @@ def main():
     print("operator on the GPU in %.2f s (n = %d, padded %d)" % (time.time() - t0, n, 4 * n))
     precond = None
     if args.precond == "conv":
-        import scipy.sparse as sp
         from fast_solver_lippmann_schwinger_b200 import sparsifier
         t0 = time.time()
-        cache = sparsifier.entriesSparseAConv(k, X, Y, fastconv, n, n, strict=False)
-        As = sparsifier.buildSparseAConv(k, X, Y, fastconv, n, n, strict=False, _cache=cache)
-        AG = sparsifier.buildSparseAGConv(k, X, Y, fastconv, n, n, strict=False, _cache=cache)
-        Msp = (As + k ** 2 * (AG @ sp.diags(nu))).tocsc()
+        # one sampling pass (49 unit-vector applies, rows and Gram matrices kept on the device), then
+        # As = buildSparseAConv(...), Mapproxsp = As + k^2 buildSparseAGConv(...) diag(nu)   (example.jl:64-67)
+        As, Msp = sparsifier.sparsifying_matrices_2d(k, X, Y, fastconv, n, n, nu, strict=False)
         print("As, Mapproxsp from GPU applies in %.2f s" % (time.time() - t0))
-        precond = ls.SparsifyingPreconditioner(Msp, As)
+        t0 = time.time()
+        precond = (ls.SparsifyingPreconditioner(Msp, As, solverType="GPU", grid=(n, n)) if args.msp == "gpu"
+                   else ls.SparsifyingPreconditioner(Msp, As))
+        print("SparsifyingPreconditioner(Mapproxsp, As) with lu(Mapproxsp) on the %s in %.2f s" % (args.msp, time.time() - t0))
     elif args.precond:
         import scipy.sparse as sp
         d = np.load(args.precond)
         N = n * n
         As = sp.csc_matrix((d["As_nzval"], d["As_rowval"] - 1, d["As_colptr"] - 1), shape=(N, N))
         Msp = sp.csc_matrix((d["Msp_nzval"], d["Msp_rowval"] - 1, d["Msp_colptr"] - 1), shape=(N, N))
-        precond = ls.SparsifyingPreconditioner(Msp, As)
+        precond = (ls.SparsifyingPreconditioner(Msp, As, solverType="GPU", grid=(n, n)) if args.msp == "gpu"
+                   else ls.SparsifyingPreconditioner(Msp, As))
     u_inc = np.exp(1j * k * X)
     rhs = -k ** 2 * ls.FFTconvolution(fastconv, nu * u_inc)          # example.jl:77
     u = np.zeros(n * n, dtype=np.complex128)
