@@ -782,7 +782,7 @@ int Msp::tune_sweeps() {
     const size_t flush_bytes = factor_bytes > ((size_t)64 << 20) ? ((size_t)192 << 20) : 0;    // small factors live in the L2 anyway
     if ((rc = dmalloc((void**)&f, vb))) return rc;
     if ((rc = dmalloc((void**)&u, vb))) return rc;
-    if (flush_bytes && (rc = dmalloc(&flush, flush_bytes))) return rc;
+    if (flush_bytes && dmalloc(&flush, flush_bytes) != LS_OK) flush = nullptr;      // no room for the flush buffer: time warm
     LS_CUDA_TRY(cudaMemsetAsync(f, 0, vb, s));
     LS_CUDA_TRY(cudaMemsetAsync(u, 0, vb, s));
     for (Level& L : lev) {
