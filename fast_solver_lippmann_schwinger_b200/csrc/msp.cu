@@ -790,9 +790,13 @@ int Msp::tune_sweeps() {
         LS_CUDA_TRY(cudaMemsetAsync(L.d_z, 0, (size_t)L.count * L.Sp * sizeof(cd), s));
         LS_CUDA_TRY(cudaMemsetAsync(L.d_t, 0, std::max<size_t>((size_t)L.count * L.Bp, 1) * sizeof(cd), s));
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    LS_CUDA_TRY(cudaEventCreate(&e0));
-    LS_CUDA_TRY(cudaEventCreate(&e1));
+    struct Events {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    LS_CUDA_TRY(cudaEventCreate(&ev.a));
+    LS_CUDA_TRY(cudaEventCreate(&ev.b));
+    const cudaEvent_t e0 = ev.a, e1 = ev.b;
     auto tune_one = [&](int d, int which, lsmsp::Choice& best) -> int {
         lsmsp::Gemv2 a;
         sweep_args(d, which, f, u, a);
@@ -829,7 +833,6 @@ int Msp::tune_sweeps() {
         if (rc == LS_OK && lev[d].Bp > 0) rc = tune_one(d, 1, lev[d].ch_fbs);
     }
     for (int d = 0; d <= D && rc == LS_OK; ++d) rc = tune_one(d, 2, lev[d].ch_y);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (rc == LS_OK) {
         cudaError_t ce = cudaStreamSynchronize(s);
         if (ce == cudaSuccess) ce = cudaGetLastError();
